@@ -1,0 +1,215 @@
+/*
+ * mceik_b200.h -- C ABI of libmceik_b200.so: the B200 (sm_100a) implementation of mceik's
+ * forward-model / location hot path (fast-sweeping eikonal solver + L2 travel-time-table
+ * grid search).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Two groups of entry points:
+ *   (1) DROP-IN symbols: the names, argument order, by-reference/by-value convention and
+ *       ierr behaviour of the reference's own C / Fortran BIND(C) interface for this path.
+ *       Each declaration cites the reference interface it replaces (file:line under the
+ *       reference tree).  An unmodified module.F90 / homog.c links against them.
+ *   (2) BATCHED extensions (mceik_*): many fields / many events per call, host- or
+ *       device-resident buffers.  The drop-in symbols are batch-of-one wrappers over these.
+ *
+ * There is NO CPU fallback: every compute entry point returns ierr/-rc != 0 (and
+ * mceik_last_error() says why) when no CUDA device is usable.
+ *
+ * Grid convention (fsm3d.f90:1936-1938, homog.c:585-587): x fastest,
+ *   flat (0-based) index = iz*nx*ny + iy*nx + ix ; z is up, z=0 is the model base.
+ */
+#ifndef MCEIK_B200_H
+#define MCEIK_B200_H 1
+
+#include <stddef.h>
+#include "mceik_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================================== */
+/* (1) DROP-IN ENTRY POINTS                                                              */
+/* ===================================================================================== */
+
+/* --- eikonal, serial life-cycle.  Replaces EIKONAL3D_SERIAL_DRIVER, declared at
+ *     module.F90:369-382, defined at fsm3d.f90:1968-2052.  job 1 = initialise for (nx,ny,nz),
+ *     job 2 = boundary conditions + fast sweeping, job 3 = finalise.  ierr: 0 ok; 1 on double
+ *     init, solve-before-init, a source whose stencil leaves the grid (fsm3d.f90:716-755), or
+ *     any CUDA failure.  Non-convergence after maxit iterations is NOT an error.             */
+void eikonal3d_serial_driver(const int *job, const int *iverb, const int *maxit, const int *nsrc,
+                             const int *nx, const int *ny, const int *nz,
+                             const double *tol, const double *h,
+                             const double *x0, const double *y0, const double *z0,
+                             const double *ts, const double *xs, const double *ys, const double *zs,
+                             const double *slow, double *u, int *ierr);
+
+/* --- eikonal, "distributed" life-cycle.  Replaces EIKONAL3D_INITIALIZE (module.F90:344-356,
+ *     fsm3d.f90:1583-1674), EIKONAL3D_SOLVE (module.F90:358-367, fsm3d.f90:1754-1840) and
+ *     EIKONAL3D_FINALIZE (module.F90:384-389, fsm3d.f90:1891-1929).  `comm` (a Fortran MPI
+ *     handle in the reference) is accepted and ignored: a field is never split across GPUs
+ *     here, so ndivx/ndivy/ndivz/noverlap are recorded but unused and the solve has the
+ *     SERIAL sweep semantics (the fixed point the reference's block-Jacobi MPI variant
+ *     converges to).  `n` must equal nx*ny*nz on the calling process.                        */
+void eikonal3d_initialize(const int *comm, const int *iverb, const int *nx, const int *ny, const int *nz,
+                          const int *ndivx, const int *ndivy, const int *ndivz,
+                          const int *noverlap, const int *maxit,
+                          const double *x0, const double *y0, const double *z0,
+                          const double *h, const double *tol, int *ierr);
+void eikonal3d_solve(const int *comm, const int *nsrc, const int *n,
+                     const double *ts, const double *xs, const double *ys, const double *zs,
+                     const double *slow, double *u, int *ierr);
+void eikonal3d_finalize(const int *comm, int *ierr);
+
+/* --- L2 grid search, C flavour.  Replaces locate_l2_gridSearch__double64 (locate.c:923-1047)
+ *     and locate_l2_gridSearch__float64 (locate.c:1079-1203): same argument checks (ldgrd
+ *     bytes % 64, ldgrd >= ngrd, nobs >= 1, NULLs, 64-byte alignment of t0/test/objfn), same
+ *     return code (0 ok, 1 error).  mask[i]==0 means "use pick i"; tcorr may be NULL.        */
+int locate_l2_gridSearch__double64(const int ldgrd, const int ngrd, const int nobs, const int iwantOT,
+                                   const double t0use, const int *mask, const double *tobs,
+                                   const double *tcorr, const double *varobs, const double *test,
+                                   double *t0, double *objfn);
+int locate_l2_gridSearch__float64(const int ldgrd, const int ngrd, const int nobs, const int iwantOT,
+                                  const float t0use, const int *mask, const float *tobs,
+                                  const float *tcorr, const float *varobs, const float *test,
+                                  float *t0, float *objfn);
+/* first index of the strict minimum (locate.c:811-851) */
+int locate_minLocDouble64(const int n, const double *x);
+int locate_minLocFloat64(const int n, const float *x);
+
+/* --- L2 grid search, Fortran flavour.  Replaces LOCATE3D_GRIDSEARCH_DOUBLE64 /
+ *     LOCATE3D_GRIDSEARCH_FLOAT64 (interface gridsearch.f90:2-26, bodies :382-459, :463-540):
+ *     by-reference arguments, mask==1 skips, t0 weight 1/(var_i * sum var), result in logPDF
+ *     (a positive misfit despite its name).  ierr = 1 when ldgrd % 64 != 0 (in ELEMENTS),
+ *     ngrd > ldgrd, every pick masked, or |sum varobs| < epsilon.                            */
+void locate3d_gridsearch__double64(const int *ldgrd, const int *ngrd, const int *nobs, const int *iwantOT,
+                                   const int *mask, const double *tobs, const double *varobs,
+                                   const double *test, double *logPDF, int *ierr);
+void locate3d_gridsearch__float64(const int *ldgrd, const int *ngrd, const int *nobs, const int *iwantOT,
+                                  const int *mask, const float *tobs, const float *varobs,
+                                  const float *test, float *logPDF, int *ierr);
+
+/* --- catalogue locator.  Replaces LOCATE3D_INITIALIZE / LOCATE3D_GRIDSEARCH /
+ *     LOCATE3D_FINALIZE (include/locate.h:10-23, locate.f90:322-519, :562-689).
+ *     The reference pulls every table from HDF5 inside its event loop (locate.f90:400,443);
+ *     HDF5 stays host-side, so here the tables and node coordinates are handed over once with
+ *     mceik_locate_set_tables() / mceik_locate_set_grid() (by the host's h5io reader) between
+ *     locate3d_initialize and locate3d_gridsearch; tttFileID/locFileID are recorded only.
+ *     job 1 = location with fixed origin time tori, job 2 = location + analytic origin time,
+ *     other jobs -> ierr = 1 ("Not yet done", locate.f90:502-512).  hypo = (x,y,z,t0) per
+ *     event.  `test` (declared OUT, never written by the reference) is left untouched.       */
+void locate3d_initialize(const int *comm, const int *iverb, const long *tttFileID, const long *locFileID,
+                         const int *ndivx, const int *ndivy, const int *ndivz, int *ierr);
+void locate3d_gridsearch(const int *model, const int *job, const int *nobs, const int *nevents,
+                         const int *luseObs, const int *statPtr, const int *pickType,
+                         const double *statCor, const double *tori, const double *varobs,
+                         const double *tobs, double *test, double *hypo, int *ierr);
+void locate3d_finalize(void);
+
+/* --- analytic homogeneous table.  Replaces computeHomogeneousTraveltimes (homog.c:594-621). */
+int computeHomogeneousTraveltimes(const int nx, const int ny, const int nz,
+                                  double x0, double y0, double z0,
+                                  const double dx, double dy, const double dz,
+                                  const double xs, const double ys, double zs,
+                                  const double vel, double *ttimes);
+
+/* ===================================================================================== */
+/* (2) BATCHED EXTENSIONS                                                                */
+/* ===================================================================================== */
+
+typedef struct mceik_ctx mceik_ctx; /* opaque: device id, stream, workspaces, resident tables */
+
+/* Last error text of the calling thread ("" if none). */
+const char *mceik_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long mceik_kernel_launch_count(void);
+
+/* device < 0 selects the current CUDA device.  stream is a cudaStream_t passed as void*
+ * (NULL = a private non-blocking stream owned by the context). */
+int mceik_ctx_create(int device, void *stream, mceik_ctx **ctx);
+void mceik_ctx_destroy(mceik_ctx *ctx);
+int mceik_ctx_synchronize(mceik_ctx *ctx);
+
+/* Geometry + solver parameters of one batch of eikonal fields (solverParametersType,
+ * module.F90:117-131, minus the MPI decomposition). */
+typedef struct mceik_fsm_grid {
+    int nx, ny, nz;
+    double h;          /* isotropic spacing (m); the solver has a single h (fsm3d.f90:2021) */
+    double x0, y0, z0; /* origin (m) */
+    double tol;        /* convergence tolerance (s) */
+    int maxit;         /* iteration cap; one iteration = 8 sweeps */
+} mceik_fsm_grid;
+
+enum { MCEIK_FSM_ALGO_TILES = 0, MCEIK_FSM_ALGO_LEVELS = 1 };
+
+/*
+ * Solve `nfields` independent eikonal fields in one call.
+ *   slow        [nmodels][N] fp64 slowness (s/m), N = nx*ny*nz
+ *   field_model [nfields]    which slowness model field f uses
+ *   src_ptr     [nfields+1]  CSR into ts/xs/ys/zs (HOST arrays in both variants): the sources
+ *                            (normally one station) that seed field f
+ *   u           [nfields][N] fp64 travel times out (may be NULL if only tables are wanted)
+ *   tables      [nfields][ldtab] fp32 travel-time tables out (may be NULL), ldtab >= N
+ *   iters       [nfields]    iterations executed per field (host, may be NULL)
+ *   field_ierr  [nfields]    per-field status: 0 ok, 1 = source stencil out of grid (host, may be NULL)
+ * Returns 0 when every field solved, 1 when some field failed (field_ierr says which), <0 on
+ * argument / CUDA errors.  _host takes host pointers and stages through the context's device
+ * workspace; _dev takes device pointers for slow/u/tables and runs on the context stream
+ * without synchronising the caller except for the small per-iteration convergence read-back.
+ */
+int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *slow,
+                                 int nfields, const int *field_model, const int *src_ptr,
+                                 const double *ts, const double *xs, const double *ys, const double *zs,
+                                 double *u, float *tables, size_t ldtab, int *iters, int *field_ierr);
+int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow,
+                                int nfields, const int *field_model, const int *src_ptr,
+                                const double *ts, const double *xs, const double *ys, const double *zs,
+                                double *d_u, float *d_tables, size_t ldtab, int *iters, int *field_ierr);
+/* Select the sweep kernel (default MCEIK_FSM_ALGO_TILES). */
+int mceik_fsm_set_algo(mceik_ctx *ctx, int algo);
+/* Node-updates executed by the last solve on this context (N * 8 * iterations, summed over fields). */
+long long mceik_fsm_last_node_updates(mceik_ctx *ctx);
+
+/* Analytic homogeneous tables on the device: fp32 table t = dist/vel per station (homog.c:594-621
+ * followed by homog.c:624-635).  d_tables [nstations][ldtab]; xs,ys,zs,vel are host arrays. */
+int mceik_homogeneous_tables_dev(mceik_ctx *ctx, int nx, int ny, int nz, double x0, double y0, double z0,
+                                 double dx, double dy, double dz, int nstations, const double *xs,
+                                 const double *ys, const double *zs, const double *vel,
+                                 float *d_tables, size_t ldtab);
+
+/* Travel-time tables resident for the locator: fp32 [ntables][ldgrd], table id =
+ * 2*(station-1) + (pickType-1) for the catalogue entry points.  _host copies, _dev borrows the
+ * caller's device buffer (it must outlive the context or the next set call). */
+int mceik_locate_set_tables_host(mceik_ctx *ctx, int ntables, int ngrd, size_t ldgrd, const float *tables);
+int mceik_locate_set_tables_dev(mceik_ctx *ctx, int ntables, int ngrd, size_t ldgrd, const float *d_tables);
+/* Node coordinates (fp32, as read from /Model/{x,y,z}locs, locate.f90:646-652), host arrays [ngrd]. */
+int mceik_locate_set_grid(mceik_ctx *ctx, int ngrd, const float *xlocs, const float *ylocs, const float *zlocs);
+/* Same for the process-global context used by the drop-in locate3d_* symbols. */
+int mceik_locate3d_set_tables(int ntables, int ngrd, size_t ldgrd, const float *tables);
+int mceik_locate3d_set_grid(int ngrd, const float *xlocs, const float *ylocs, const float *zlocs);
+
+/*
+ * Locate a batch of events against the resident tables (CSR picks).
+ *   obs_ptr  [nevents+1]; per pick: table id (<0 = unused), corrected pick time
+ *   (tobs - static correction), variance.  job 1: t0 fixed to tori[e]; job 2: analytic t0.
+ *   Outputs per event: iopt (0-based flat node, -1 when the event has no usable pick),
+ *   t0opt (origin time at iopt), objopt (objective at iopt).
+ * _host: all pointers host.  _dev: all pointers device, asynchronous on the context stream;
+ *   nobs_total = obs_ptr[nevents], max_picks = an upper bound on picks per event (sizes smem).
+ */
+int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *obs_ptr, const int *table_id,
+                              const double *tobs_cor, const double *varobs, const double *tori,
+                              int *iopt, double *t0opt, double *objopt);
+int mceik_locate_batched_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_picks, const int *d_obs_ptr,
+                             const int *d_table_id, const double *d_tobs_cor, const double *d_varobs,
+                             const double *d_tori, int *d_iopt, double *d_t0opt, double *d_objopt);
+/* Catalogue form (mceik_struct.h layouts): picks are catalog->obsPtr CSR, table from
+ * (statPtr, pickType), static correction from stations->pcorr/scorr; hypo[4*nevents] needs
+ * mceik_locate_set_grid().  iopt/obj may be NULL. */
+int mceik_locate_catalog(mceik_ctx *ctx, const struct mceik_catalog_struct *catalog,
+                         const struct mceik_stations_struct *stations, int job,
+                         double *hypo, int *iopt, double *obj);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCEIK_B200_H */

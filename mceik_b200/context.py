@@ -1,0 +1,37 @@
+"""Opaque per-process / per-GPU context of libmceik_b200 (device, stream, workspaces, tables)."""
+import ctypes as C
+
+from . import _lib
+
+
+class Context:
+    """Owns one ``mceik_ctx``.  ``device`` < 0 means the current CUDA device; ``stream`` may be a
+    raw ``cudaStream_t`` integer (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+
+    def __init__(self, device=-1, stream=None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.mceik_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise _lib.MceikError(f"mceik_ctx_create failed (rc={rc}): {_lib.last_error()}")
+        self.handle = h
+
+    def synchronize(self):
+        _lib.check(self._lib.mceik_ctx_synchronize(self.handle), "mceik_ctx_synchronize")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.mceik_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -1,0 +1,929 @@
+// abi.cu -- the C ABI of libmceik_b200.so (declared in include/mceik_b200.h).
+//
+// Host-side orchestration only: argument checks that mirror the reference entry points,
+// staging between caller memory and HBM, the per-iteration convergence loop of the eikonal
+// solver, and the batch-of-one wrappers behind the drop-in symbols.  All arithmetic on grid-
+// sized data happens in the kernels of fsm.cu / gs.cu; there is no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/mceik_b200.h"
+#include "common.cuh"
+#include "fsm.cuh"
+#include "gs.cuh"
+#include "host_logic.hpp"
+
+namespace mceik {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *last_error() { return g_err; }
+static std::atomic<long long> g_launches{0};
+void count_launch(long long n) { g_launches += n; }
+long long launch_count() { return g_launches.load(); }
+
+}  // namespace mceik
+
+using namespace mceik;
+
+struct mceik_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int fsm_algo = MCEIK_FSM_ALGO_TILES;
+    long long last_updates = 0;
+    fsm::TilePlan plan;
+    // eikonal workspaces
+    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
+    // locator state
+    const float *d_tables = nullptr;
+    DevBuf own_tables;
+    int ntables = 0, ngrd = 0;
+    size_t ldgrd = 0;
+    std::vector<float> xlocs, ylocs, zlocs;
+    DevBuf ws_gs_in, ws_gs_w, ws_gs_part, ws_gs_out, ws_gs_misc;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) MCEIK_CUDA(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class F>
+int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::exception &e) {
+        set_error("%s", e.what());
+        return -2;
+    }
+}
+
+template <class T>
+T *upload(DevBuf &buf, size_t offset_bytes, const std::vector<T> &v, cudaStream_t st) {
+    T *d = reinterpret_cast<T *>(static_cast<char *>(buf.p) + offset_bytes);
+    if (!v.empty()) MCEIK_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return d;
+}
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// eikonal: the batched solve on device-resident slow / u
+// ------------------------------------------------------------------------------------------
+int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const double *d_slow, int nfields,
+                  const int *field_model, const int *src_ptr, const double *ts, const double *xs,
+                  const double *ys, const double *zs, double *d_u, float *d_tables, size_t ldtab, int *iters,
+                  int *field_ierr) {
+    if (!ctx || !g || !d_slow || !field_model || !src_ptr || (nfields > 0 && (!ts || !xs || !ys || !zs))) {
+        set_error("mceik_fsm_solve_batched: NULL argument");
+        return -1;
+    }
+    if (g->nx < 1 || g->ny < 1 || g->nz < 1 || nmodels < 1 || nfields < 0 || nfields > 65535) {
+        set_error("mceik_fsm_solve_batched: bad sizes (nx,ny,nz >= 1, 0 <= nfields <= 65535)");
+        return -1;
+    }
+    const size_t N = (size_t)g->nx * g->ny * g->nz;
+    if (N > (size_t)INT_MAX) {
+        set_error("mceik_fsm_solve_batched: grid has more than 2^31-1 nodes");
+        return -1;
+    }
+    if (d_tables && ldtab < N) {
+        set_error("mceik_fsm_solve_batched: ldtab < nx*ny*nz");
+        return -1;
+    }
+    for (int f = 0; f < nfields; ++f)
+        if (field_model[f] < 0 || field_model[f] >= nmodels) {
+            set_error("mceik_fsm_solve_batched: field_model[%d] out of range", f);
+            return -1;
+        }
+    ctx->last_updates = 0;
+    if (nfields == 0) return 0;
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const int nx = g->nx, ny = g->ny, nz = g->nz;
+
+    if (!d_u) d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * nfields));
+    double *d_u0 = static_cast<double *>(ctx->ws_u0.ensure(sizeof(double) * N * nfields));
+    ctx->plan.build(nx, ny, nz, st);
+    const fsm::TilePlan &pl = ctx->plan;
+
+    // ---- boundary conditions: stencil records per field (host), unique node lists per field
+    std::vector<fsm::BcRecord> recs;
+    std::vector<int> rec_ptr(nfields + 1, 0), ferr(nfields, 0);
+    std::vector<int> bc_ptr(nfields + 1, 0), bc_tile, rec_field, rec_node;
+    std::vector<uint16_t> bc_local;
+    for (int f = 0; f < nfields; ++f) {
+        const int s0 = src_ptr[f], ns = src_ptr[f + 1] - src_ptr[f];
+        const size_t before = recs.size();
+        ferr[f] = ns < 0 ? 1 : host::build_bc_records(nx, ny, nz, g->h, g->x0, g->y0, g->z0, ns, ts + s0, xs + s0,
+                                                      ys + s0, zs + s0, recs);
+        if (ferr[f]) recs.resize(before);  // SETBCS failed: the field is not solved (fsm3d.f90:2022-2026)
+        rec_ptr[f + 1] = (int)recs.size();
+        std::vector<int> nodes;
+        for (size_t r = before; r < recs.size(); ++r) nodes.push_back(recs[r].node);
+        std::sort(nodes.begin(), nodes.end());
+        nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+        for (int node : nodes) {
+            const int ix = node % nx, iy = (node / nx) % ny, iz = node / (nx * ny);
+            const int I = ix / fsm::kTile, J = iy / fsm::kTile, K = iz / fsm::kTile;
+            bc_tile.push_back((K * pl.nty + J) * pl.ntx + I);
+            bc_local.push_back((uint16_t)((ix % fsm::kTile) | ((iy % fsm::kTile) << 4) | ((iz % fsm::kTile) << 8)));
+            rec_field.push_back(f);
+            rec_node.push_back(node);
+        }
+        bc_ptr[f + 1] = (int)bc_tile.size();
+    }
+    std::vector<int> fmodel(field_model, field_model + nfields);
+
+    // meta buffer layout (all offsets 256-byte aligned)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    const size_t o_fmodel = take(sizeof(int) * nfields), o_recptr = take(sizeof(int) * (nfields + 1));
+    const size_t o_recs = take(sizeof(fsm::BcRecord) * std::max<size_t>(recs.size(), 1));
+    const size_t o_bcptr = take(sizeof(int) * (nfields + 1)), o_bctile = take(sizeof(int) * std::max<size_t>(bc_tile.size(), 1));
+    const size_t o_bcloc = take(sizeof(uint16_t) * std::max<size_t>(bc_local.size(), 1));
+    const size_t o_recf = take(sizeof(int) * std::max<size_t>(rec_field.size(), 1));
+    const size_t o_recn = take(sizeof(int) * std::max<size_t>(rec_node.size(), 1));
+    const size_t o_gfields = take(sizeof(int) * fsm::kMaxSlots * nfields), o_gmodel = take(sizeof(int) * nfields);
+    const size_t o_active = take(sizeof(int) * nfields);
+    ctx->ws_meta.ensure(off);
+    const int *d_fmodel = upload(ctx->ws_meta, o_fmodel, fmodel, st);
+    const int *d_recptr = upload(ctx->ws_meta, o_recptr, rec_ptr, st);
+    const fsm::BcRecord *d_recs = upload(ctx->ws_meta, o_recs, recs, st);
+    const int *d_bcptr = upload(ctx->ws_meta, o_bcptr, bc_ptr, st);
+    const int *d_bctile = upload(ctx->ws_meta, o_bctile, bc_tile, st);
+    const uint16_t *d_bcloc = upload(ctx->ws_meta, o_bcloc, bc_local, st);
+    const int *d_recf = upload(ctx->ws_meta, o_recf, rec_field, st);
+    const int *d_recn = upload(ctx->ws_meta, o_recn, rec_node, st);
+
+    // ---- u = HUGE everywhere, then the stencil values (fsm3d.f90:782-834)
+    fsm::launch_fill(d_u, N * nfields, DBL_MAX, st);
+    fsm::launch_apply_bcs(nfields, N, d_fmodel, d_recptr, d_recs, d_slow, d_u, st);
+
+    // ---- iterations (fsm3d.f90:62-96).  One launch = 8 sweeps of every still-active field.
+    std::vector<int> active, it(nfields, 0);
+    for (int f = 0; f < nfields; ++f)
+        if (!ferr[f]) active.push_back(f);
+    // control block: [queue int (256 B)] [nonconv ull x nfields] [done int x ngroups*ntiles]
+    const size_t c_nonconv = 256, c_done = align_up(c_nonconv + sizeof(unsigned long long) * nfields);
+    ctx->ws_ctrl.ensure(c_done + sizeof(int) * (size_t)nfields * pl.ntiles);
+    char *ctrl = static_cast<char *>(ctx->ws_ctrl.p);
+    unsigned long long *d_nonconv = reinterpret_cast<unsigned long long *>(ctrl + c_nonconv);
+    std::vector<unsigned long long> h_nonconv(nfields);
+
+    uint8_t *d_lupd = nullptr;
+    if (ctx->fsm_algo == MCEIK_FSM_ALGO_LEVELS) {
+        d_lupd = static_cast<uint8_t *>(ctx->ws_lupd.ensure(N * nfields));
+        MCEIK_CUDA(cudaMemsetAsync(d_lupd, 1, N * nfields, st));
+        fsm::launch_mark_bcs((int)rec_field.size(), d_recf, d_recn, N, d_lupd, st);
+        MCEIK_CUDA(cudaMemcpyAsync(d_u0, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToDevice, st));
+    }
+
+    for (int k = 1; k <= g->maxit && !active.empty(); ++k) {
+        MCEIK_CUDA(cudaMemsetAsync(ctrl, 0, c_done, st));
+        if (ctx->fsm_algo == MCEIK_FSM_ALGO_LEVELS) {
+            const int *d_active = upload(ctx->ws_meta, o_active, active, st);
+            fsm::launch_iteration_levels(nx, ny, nz, g->h, (int)active.size(), d_active, d_fmodel, d_slow, d_lupd,
+                                         d_u, st);
+            fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
+        } else {
+            // group the active fields by slowness model, up to kMaxSlots per CTA
+            std::map<int, std::vector<int>> by_model;
+            for (int f : active) by_model[fmodel[f]].push_back(f);
+            size_t widest = 0;
+            for (auto &kv : by_model) widest = std::max(widest, kv.second.size());
+            const int B = widest >= 3 ? 4 : (widest == 2 ? 2 : 1);
+            std::vector<int> gfields, gmodel;
+            for (auto &kv : by_model)
+                for (size_t i = 0; i < kv.second.size(); i += B) {
+                    gmodel.push_back(kv.first);
+                    for (int b = 0; b < fsm::kMaxSlots; ++b)
+                        gfields.push_back(b < B && i + b < kv.second.size() ? kv.second[i + b] : -1);
+                }
+            const int ngroups = (int)gmodel.size();
+            if ((long long)ngroups * pl.ntiles * 8 > (long long)INT_MAX) throw CudaError("too many tile tasks in one launch");
+            fsm::SweepArgs a;
+            a.nx = nx; a.ny = ny; a.nz = nz;
+            a.ntx = pl.ntx; a.nty = pl.nty; a.ntz = pl.ntz; a.ntiles = pl.ntiles; a.ntlevels = pl.ntlevels;
+            a.ngroups = ngroups; a.nslots = B;
+            a.h = g->h; a.tol = g->tol;
+            a.group_fields = upload(ctx->ws_meta, o_gfields, gfields, st);
+            a.group_model = upload(ctx->ws_meta, o_gmodel, gmodel, st);
+            a.slow = d_slow; a.u = d_u; a.u0 = d_u0;
+            a.tile_order = ctx->plan.tile_order.as<int>();
+            a.tlevel_ptr = ctx->plan.tlevel_ptr.as<int>();
+            a.lvl_nodes = ctx->plan.lvl_nodes.as<uint16_t>();
+            a.queue = reinterpret_cast<int *>(ctrl);
+            a.nonconv = d_nonconv;
+            a.done = reinterpret_cast<int *>(ctrl + c_done);
+            a.bc_ptr = d_bcptr; a.bc_tile = d_bctile; a.bc_local = d_bcloc;
+            MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)ngroups * pl.ntiles, st));
+            fsm::launch_iteration_tiles(a, st);
+        }
+        MCEIK_CUDA(cudaMemcpyAsync(h_nonconv.data(), d_nonconv, sizeof(unsigned long long) * nfields,
+                                   cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> still;
+        for (int f : active) {
+            it[f] = k;
+            if (h_nonconv[f] != 0) still.push_back(f);  // lconv /= nxyz -> next iteration (fsm3d.f90:95)
+        }
+        active.swap(still);
+    }
+    int rc = 0;
+    for (int f = 0; f < nfields; ++f) {
+        ctx->last_updates += (long long)N * 8 * it[f];
+        if (iters) iters[f] = it[f];
+        if (field_ierr) field_ierr[f] = ferr[f];
+        if (ferr[f]) rc = 1;
+    }
+    if (d_tables) fsm::launch_pack_tables(nfields, N, ldtab, d_u, d_tables, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// locator: batched search on device-resident pick arrays
+// ------------------------------------------------------------------------------------------
+int locate_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_picks, const int *d_obs_ptr,
+               const int *d_table_id, const double *d_tobs_cor, const double *d_varobs, const double *d_tori,
+               int *d_iopt, double *d_t0opt, double *d_objopt) {
+    if (!ctx || !ctx->d_tables) {
+        set_error("mceik_locate_batched: no travel-time tables set");
+        return -1;
+    }
+    if (job != 1 && job != 2) {
+        set_error("mceik_locate_batched: job %d not supported (1 = fixed origin time, 2 = analytic origin time)", job);
+        return 1;
+    }
+    if (nevents < 0 || nobs_total < 0 || max_picks < 0 || !d_obs_ptr || (job == 1 && !d_tori) || !d_iopt || !d_t0opt ||
+        !d_objopt) {
+        set_error("mceik_locate_batched: bad argument");
+        return -1;
+    }
+    if (nevents == 0) return 0;
+    DeviceGuard dg(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t np = std::max(nobs_total, 1);
+    double *d_w = static_cast<double *>(ctx->ws_gs_w.ensure(align_up(sizeof(double) * np) * 2 + sizeof(int) * nevents));
+    double *d_w0 = d_w;
+    double *d_w1 = reinterpret_cast<double *>(reinterpret_cast<char *>(d_w) + align_up(sizeof(double) * np));
+    int *d_nuse = reinterpret_cast<int *>(reinterpret_cast<char *>(d_w) + 2 * align_up(sizeof(double) * np));
+    gs::launch_prepare(nevents, d_obs_ptr, d_table_id, d_varobs, d_w0, d_w1, d_nuse, st);
+    const int max_events_per_launch = 65535 * gs::kEventsPerBlock;
+    for (int e0 = 0; e0 < nevents; e0 += max_events_per_launch) {
+        const int ne = std::min(max_events_per_launch, nevents - e0);
+        gs::LocateArgs a;
+        a.job = job; a.nevents = ne; a.ngrd = ctx->ngrd; a.ldgrd = ctx->ldgrd; a.maxpicks = std::max(max_picks, 1);
+        a.tables = ctx->d_tables;
+        a.obs_ptr = d_obs_ptr + e0; a.table_id = d_table_id; a.tobs_cor = d_tobs_cor; a.w_t0 = d_w0; a.w_obj = d_w1;
+        a.tori = d_tori ? d_tori + e0 : nullptr;
+        a.nlanes = gs::locate_lanes(ne, ctx->ngrd);
+        a.partials = static_cast<gs::Partial *>(ctx->ws_gs_part.ensure(sizeof(gs::Partial) * (size_t)ne * a.nlanes));
+        gs::launch_locate(a, st);
+        gs::launch_finalize(ne, a.nlanes, a.partials, d_nuse + e0, d_iopt + e0, d_t0opt + e0, d_objopt + e0, st);
+    }
+    return 0;
+}
+
+std::mutex g_mutex;
+mceik_ctx *g_default_ctx = nullptr;
+
+mceik_ctx *default_ctx() {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!g_default_ctx) {
+        mceik_ctx *c = nullptr;
+        if (mceik_ctx_create(-1, nullptr, &c) != 0) return nullptr;
+        g_default_ctx = c;
+    }
+    return g_default_ctx;
+}
+
+// hidden state of the drop-in life-cycles (the reference keeps SAVE / module variables:
+// fsm3d.f90:1985-1988, module.F90:419-423, 469-470)
+struct SerialState { bool init = false; int nx = 0, ny = 0, nz = 0; } g_serial;
+struct SolveState { bool init = false; mceik_fsm_grid grid{}; } g_solve;
+struct LocState { bool init = false; int iverb = 0; } g_loc;
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+const char *mceik_last_error(void) { return mceik::last_error(); }
+long long mceik_kernel_launch_count(void) { return mceik::launch_count(); }
+
+int mceik_ctx_create(int device, void *stream, mceik_ctx **out) {
+    return guarded([&]() -> int {
+        if (!out) { set_error("mceik_ctx_create: NULL out"); return -1; }
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            set_error("mceik_ctx_create: no CUDA device (%s); libmceik_b200 has no CPU fallback", cudaGetErrorString(e));
+            cudaGetLastError();
+            return -3;
+        }
+        if (device < 0) MCEIK_CUDA(cudaGetDevice(&device));
+        if (device >= ndev) { set_error("mceik_ctx_create: device %d of %d", device, ndev); return -1; }
+        cudaDeviceProp prop;
+        MCEIK_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            set_error("mceik_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+            return -3;
+        }
+        DeviceGuard dg(device);
+        mceik_ctx *c = new mceik_ctx();
+        c->device = device;
+        if (stream) {
+            c->stream = static_cast<cudaStream_t>(stream);
+        } else {
+            MCEIK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            c->own_stream = true;
+        }
+        *out = c;
+        return 0;
+    });
+}
+
+void mceik_ctx_destroy(mceik_ctx *c) {
+    if (!c) return;
+    try {
+        DeviceGuard dg(c->device);
+        cudaStreamSynchronize(c->stream);
+        c->plan.release();
+        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv,
+                          &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
+            b->release();
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+    } catch (...) {
+    }
+    delete c;
+}
+
+int mceik_ctx_synchronize(mceik_ctx *c) {
+    return guarded([&]() -> int {
+        if (!c) return -1;
+        DeviceGuard dg(c->device);
+        MCEIK_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    });
+}
+
+int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
+    if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS)) return -1;
+    c->fsm_algo = algo;
+    return 0;
+}
+long long mceik_fsm_last_node_updates(mceik_ctx *c) { return c ? c->last_updates : 0; }
+
+int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow,
+                                int nfields, const int *field_model, const int *src_ptr, const double *ts,
+                                const double *xs, const double *ys, const double *zs, double *d_u, float *d_tables,
+                                size_t ldtab, int *iters, int *field_ierr) {
+    return guarded([&]() -> int {
+        return fsm_solve_dev(ctx, grid, nmodels, d_slow, nfields, field_model, src_ptr, ts, xs, ys, zs, d_u, d_tables,
+                             ldtab, iters, field_ierr);
+    });
+}
+
+int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *slow, int nfields,
+                                 const int *field_model, const int *src_ptr, const double *ts, const double *xs,
+                                 const double *ys, const double *zs, double *u, float *tables, size_t ldtab, int *iters,
+                                 int *field_ierr) {
+    return guarded([&]() -> int {
+        if (!ctx || !grid || !slow) { set_error("mceik_fsm_solve_batched_host: NULL argument"); return -1; }
+        if (grid->nx < 1 || grid->ny < 1 || grid->nz < 1 || nmodels < 1 || nfields < 0) {
+            set_error("mceik_fsm_solve_batched_host: bad sizes");
+            return -1;
+        }
+        DeviceGuard dg(ctx->device);
+        const size_t N = (size_t)grid->nx * grid->ny * grid->nz;
+        double *d_slow = static_cast<double *>(ctx->ws_slow.ensure(sizeof(double) * N * nmodels));
+        MCEIK_CUDA(cudaMemcpyAsync(d_slow, slow, sizeof(double) * N * nmodels, cudaMemcpyHostToDevice, ctx->stream));
+        double *d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * std::max(nfields, 1)));
+        float *d_tab = nullptr;
+        if (tables) d_tab = static_cast<float *>(ctx->ws_tab.ensure(sizeof(float) * ldtab * std::max(nfields, 1)));
+        const int rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nfields, field_model, src_ptr, ts, xs, ys, zs, d_u, d_tab,
+                                     ldtab, iters, field_ierr);
+        if (rc < 0) return rc;
+        if (u) MCEIK_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tables)
+            MCEIK_CUDA(cudaMemcpyAsync(tables, d_tab, sizeof(float) * ldtab * nfields, cudaMemcpyDeviceToHost, ctx->stream));
+        MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return rc;
+    });
+}
+
+int mceik_homogeneous_tables_dev(mceik_ctx *ctx, int nx, int ny, int nz, double x0, double y0, double z0, double dx,
+                                 double dy, double dz, int nstations, const double *xs, const double *ys, const double *zs,
+                                 const double *vel, float *d_tables, size_t ldtab) {
+    return guarded([&]() -> int {
+        if (!ctx || !xs || !ys || !zs || !vel || !d_tables || nx < 1 || ny < 1 || nz < 1 || nstations < 0 ||
+            nstations > 65535 || ldtab < (size_t)nx * ny * nz) {
+            set_error("mceik_homogeneous_tables_dev: bad argument");
+            return -1;
+        }
+        DeviceGuard dg(ctx->device);
+        std::vector<double> xyzv(4 * (size_t)nstations);
+        for (int s = 0; s < nstations; ++s) {
+            xyzv[4 * s] = xs[s]; xyzv[4 * s + 1] = ys[s]; xyzv[4 * s + 2] = zs[s];
+            xyzv[4 * s + 3] = 1.0 / vel[s];  // homog.c:604
+        }
+        ctx->ws_xyzv.ensure(sizeof(double) * std::max<size_t>(xyzv.size(), 1));
+        const double *d_xyzv = upload(ctx->ws_xyzv, 0, xyzv, ctx->stream);
+        fsm::launch_homog_tables<float>(nx, ny, nz, x0, y0, z0, dx, dy, dz, nstations, d_xyzv, d_tables, ldtab, ctx->stream);
+        MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    });
+}
+
+// ---------------------------------------------------------------- locator state
+int mceik_locate_set_tables_dev(mceik_ctx *ctx, int ntables, int ngrd, size_t ldgrd, const float *d_tables) {
+    if (!ctx || ntables < 1 || ngrd < 1 || ldgrd < (size_t)ngrd || !d_tables) {
+        set_error("mceik_locate_set_tables: bad argument");
+        return -1;
+    }
+    ctx->d_tables = d_tables; ctx->ntables = ntables; ctx->ngrd = ngrd; ctx->ldgrd = ldgrd;
+    return 0;
+}
+
+int mceik_locate_set_tables_host(mceik_ctx *ctx, int ntables, int ngrd, size_t ldgrd, const float *tables) {
+    return guarded([&]() -> int {
+        if (!ctx || ntables < 1 || ngrd < 1 || ldgrd < (size_t)ngrd || !tables) {
+            set_error("mceik_locate_set_tables: bad argument");
+            return -1;
+        }
+        DeviceGuard dg(ctx->device);
+        float *d = static_cast<float *>(ctx->own_tables.ensure(sizeof(float) * ldgrd * ntables));
+        MCEIK_CUDA(cudaMemcpyAsync(d, tables, sizeof(float) * ldgrd * ntables, cudaMemcpyHostToDevice, ctx->stream));
+        MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
+        return mceik_locate_set_tables_dev(ctx, ntables, ngrd, ldgrd, d);
+    });
+}
+
+int mceik_locate_set_grid(mceik_ctx *ctx, int ngrd, const float *xl, const float *yl, const float *zl) {
+    if (!ctx || ngrd < 1 || !xl || !yl || !zl) { set_error("mceik_locate_set_grid: bad argument"); return -1; }
+    ctx->xlocs.assign(xl, xl + ngrd); ctx->ylocs.assign(yl, yl + ngrd); ctx->zlocs.assign(zl, zl + ngrd);
+    return 0;
+}
+
+int mceik_locate3d_set_tables(int ntables, int ngrd, size_t ldgrd, const float *tables) {
+    mceik_ctx *c = default_ctx();
+    return c ? mceik_locate_set_tables_host(c, ntables, ngrd, ldgrd, tables) : -3;
+}
+int mceik_locate3d_set_grid(int ngrd, const float *xl, const float *yl, const float *zl) {
+    mceik_ctx *c = default_ctx();
+    return c ? mceik_locate_set_grid(c, ngrd, xl, yl, zl) : -3;
+}
+
+int mceik_locate_batched_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_picks, const int *d_obs_ptr,
+                             const int *d_table_id, const double *d_tobs_cor, const double *d_varobs,
+                             const double *d_tori, int *d_iopt, double *d_t0opt, double *d_objopt) {
+    return guarded([&]() -> int {
+        return locate_dev(ctx, job, nevents, nobs_total, max_picks, d_obs_ptr, d_table_id, d_tobs_cor, d_varobs, d_tori,
+                          d_iopt, d_t0opt, d_objopt);
+    });
+}
+
+int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *obs_ptr, const int *table_id,
+                              const double *tobs_cor, const double *varobs, const double *tori, int *iopt,
+                              double *t0opt, double *objopt) {
+    return guarded([&]() -> int {
+        if (!ctx || nevents < 0 || !obs_ptr || !iopt || !t0opt || !objopt) {
+            set_error("mceik_locate_batched_host: bad argument");
+            return -1;
+        }
+        if (nevents == 0) return 0;
+        if (job != 1 && job != 2) { set_error("mceik_locate_batched_host: job %d not supported", job); return 1; }
+        const int np = obs_ptr[nevents] - obs_ptr[0];
+        if (np > 0 && (!table_id || !tobs_cor || !varobs)) { set_error("mceik_locate_batched_host: NULL pick arrays"); return -1; }
+        int maxp = 0;
+        std::vector<int> optr(nevents + 1);
+        for (int e = 0; e <= nevents; ++e) optr[e] = obs_ptr[e] - obs_ptr[0];
+        for (int e = 0; e < nevents; ++e) {
+            if (optr[e + 1] < optr[e]) { set_error("mceik_locate_batched_host: obs_ptr not monotone"); return -1; }
+            maxp = std::max(maxp, optr[e + 1] - optr[e]);
+        }
+        for (int p = 0; p < np; ++p)
+            if (table_id[obs_ptr[0] + p] >= ctx->ntables) { set_error("mceik_locate_batched_host: table id out of range"); return -1; }
+        DeviceGuard dg(ctx->device);
+        cudaStream_t st = ctx->stream;
+        const size_t npp = std::max(np, 1);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+        const size_t o_ptr = take(sizeof(int) * (nevents + 1)), o_tid = take(sizeof(int) * npp);
+        const size_t o_tobs = take(sizeof(double) * npp), o_var = take(sizeof(double) * npp), o_tori = take(sizeof(double) * nevents);
+        char *in = static_cast<char *>(ctx->ws_gs_in.ensure(off));
+        MCEIK_CUDA(cudaMemcpyAsync(in + o_ptr, optr.data(), sizeof(int) * (nevents + 1), cudaMemcpyHostToDevice, st));
+        if (np > 0) {
+            MCEIK_CUDA(cudaMemcpyAsync(in + o_tid, table_id + obs_ptr[0], sizeof(int) * np, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(in + o_tobs, tobs_cor + obs_ptr[0], sizeof(double) * np, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(in + o_var, varobs + obs_ptr[0], sizeof(double) * np, cudaMemcpyHostToDevice, st));
+        }
+        if (tori) MCEIK_CUDA(cudaMemcpyAsync(in + o_tori, tori, sizeof(double) * nevents, cudaMemcpyHostToDevice, st));
+        else if (job == 1) { set_error("mceik_locate_batched_host: job 1 needs tori"); return -1; }
+        const size_t q_t0 = align_up(sizeof(int) * nevents), q_obj = q_t0 + align_up(sizeof(double) * nevents);
+        char *out = static_cast<char *>(ctx->ws_gs_out.ensure(q_obj + sizeof(double) * nevents));
+        const int rc = locate_dev(ctx, job, nevents, np, maxp, reinterpret_cast<int *>(in + o_ptr),
+                                  reinterpret_cast<int *>(in + o_tid), reinterpret_cast<double *>(in + o_tobs),
+                                  reinterpret_cast<double *>(in + o_var), reinterpret_cast<double *>(in + o_tori),
+                                  reinterpret_cast<int *>(out), reinterpret_cast<double *>(out + q_t0),
+                                  reinterpret_cast<double *>(out + q_obj));
+        if (rc != 0) return rc;
+        MCEIK_CUDA(cudaMemcpyAsync(iopt, out, sizeof(int) * nevents, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaMemcpyAsync(t0opt, out + q_t0, sizeof(double) * nevents, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaMemcpyAsync(objopt, out + q_obj, sizeof(double) * nevents, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+static void fill_hypo(const mceik_ctx *ctx, int nevents, const int *iopt, const double *t0, double *hypo) {
+    for (int e = 0; e < nevents; ++e) {
+        const int i = iopt[e];
+        if (i < 0 || (size_t)i >= ctx->xlocs.size()) {
+            hypo[4 * e] = hypo[4 * e + 1] = hypo[4 * e + 2] = hypo[4 * e + 3] = 0.0;
+        } else {  // hypo4 = (xlocs, ylocs, zlocs, t0)(iopt), locate.f90:478-481
+            hypo[4 * e] = (double)ctx->xlocs[i]; hypo[4 * e + 1] = (double)ctx->ylocs[i];
+            hypo[4 * e + 2] = (double)ctx->zlocs[i]; hypo[4 * e + 3] = t0[e];
+        }
+    }
+}
+
+int mceik_locate_catalog(mceik_ctx *ctx, const struct mceik_catalog_struct *cat, const struct mceik_stations_struct *sta,
+                         int job, double *hypo, int *iopt_out, double *obj_out) {
+    return guarded([&]() -> int {
+        if (!ctx || !cat || !sta || !hypo || cat->nevents < 0 || !cat->obsPtr) {
+            set_error("mceik_locate_catalog: bad argument");
+            return -1;
+        }
+        if ((int)ctx->xlocs.size() != ctx->ngrd) { set_error("mceik_locate_catalog: node coordinates not set"); return -1; }
+        const int ne = cat->nevents, np = cat->obsPtr[ne] - cat->obsPtr[0];
+        std::vector<int> tid(std::max(np, 1));
+        std::vector<double> tc(std::max(np, 1));
+        for (int p = cat->obsPtr[0]; p < cat->obsPtr[ne]; ++p) {
+            const int q = p - cat->obsPtr[0], stn = cat->statPtr[p], ph = cat->pickType[p];
+            if (cat->luseObs[p] == 0) { tid[q] = -1; tc[q] = 0.0; continue; }
+            if (stn < 1 || stn > sta->nstat || (ph != P_PRIMARY_PICK && ph != S_PRIMARY_PICK)) {
+                set_error("mceik_locate_catalog: pick %d has station %d / phase %d", p, stn, ph);
+                return -1;
+            }
+            tid[q] = 2 * (stn - 1) + (ph - 1);
+            const double cor = ph == P_PRIMARY_PICK ? (sta->pcorr ? sta->pcorr[stn - 1] : 0.0) : (sta->scorr ? sta->scorr[stn - 1] : 0.0);
+            tc[q] = cat->tobs[p] - cor;
+        }
+        std::vector<int> optr(ne + 1), iopt(std::max(ne, 1));
+        for (int e = 0; e <= ne; ++e) optr[e] = cat->obsPtr[e] - cat->obsPtr[0];
+        std::vector<double> t0(std::max(ne, 1)), obj(std::max(ne, 1));
+        const int rc = mceik_locate_batched_host(ctx, job, ne, optr.data(), tid.data(), tc.data(),
+                                                 cat->varObs + cat->obsPtr[0], cat->tori, iopt.data(), t0.data(), obj.data());
+        if (rc != 0) return rc;
+        fill_hypo(ctx, ne, iopt.data(), t0.data(), hypo);
+        for (int e = 0; e < ne; ++e) {
+            if (iopt_out) iopt_out[e] = iopt[e];
+            if (obj_out) obj_out[e] = obj[e];
+        }
+        return 0;
+    });
+}
+
+// ============================================================================================
+// DROP-IN SYMBOLS
+// ============================================================================================
+void eikonal3d_serial_driver(const int *job, const int *iverb, const int *maxit, const int *nsrc, const int *nx,
+                             const int *ny, const int *nz, const double *tol, const double *h, const double *x0,
+                             const double *y0, const double *z0, const double *ts, const double *xs, const double *ys,
+                             const double *zs, const double *slow, double *u, int *ierr) {
+    *ierr = 0;
+    if (*job == 1) {
+        if (g_serial.init) {
+            printf(" eikonal3d_serial_driver: Already initialized!\n");
+            *ierr = 1;
+            return;
+        }
+        mceik_ctx *c = default_ctx();
+        if (!c) { printf(" eikonal3d_serial_driver: %s\n", mceik_last_error()); *ierr = 1; return; }
+        if (*iverb > 0) printf(" eikonal3d_serial_driver: Generating levels...\n");
+        g_serial.init = true; g_serial.nx = *nx; g_serial.ny = *ny; g_serial.nz = *nz;
+    } else if (*job == 2) {
+        if (!g_serial.init) {
+            printf(" eikonal3d_serial_driver: Solver not initalized!\n");
+            *ierr = 1;
+            return;
+        }
+        mceik_ctx *c = default_ctx();
+        if (!c) { *ierr = 1; return; }
+        if (*iverb > 0) printf(" eikonal3d_serial_driver: Solving...\n");
+        mceik_fsm_grid g{*nx, *ny, *nz, *h, *x0, *y0, *z0, *tol, *maxit};
+        const int fm = 0, sp[2] = {0, *nsrc};
+        int ferr = 0;
+        const int rc = mceik_fsm_solve_batched_host(c, &g, 1, slow, 1, &fm, sp, ts, xs, ys, zs, u, nullptr, 0, nullptr, &ferr);
+        if (rc != 0) {
+            if (ferr) printf(" eikonal3d_serial_driver: Error setting boundary conditions\n");
+            else printf(" eikonal3d_serial_driver: %s\n", mceik_last_error());
+            *ierr = 1;
+        }
+    } else {
+        if (!g_serial.init) printf(" eikonal3d_serial_driver: Never initialized!\n");
+        g_serial = SerialState();
+    }
+}
+
+void eikonal3d_initialize(const int *comm, const int *iverb, const int *nx, const int *ny, const int *nz, const int *ndivx,
+                          const int *ndivy, const int *ndivz, const int *noverlap, const int *maxit, const double *x0,
+                          const double *y0, const double *z0, const double *h, const double *tol, int *ierr) {
+    (void)comm; (void)iverb; (void)ndivx; (void)ndivy; (void)ndivz; (void)noverlap;
+    *ierr = 0;
+    if (!default_ctx()) { printf(" eikonal3d_initialize: %s\n", mceik_last_error()); *ierr = 1; return; }
+    g_solve.grid = mceik_fsm_grid{*nx, *ny, *nz, *h, *x0, *y0, *z0, *tol, *maxit};
+    g_solve.init = true;
+}
+
+void eikonal3d_solve(const int *comm, const int *nsrc, const int *n, const double *ts, const double *xs, const double *ys,
+                     const double *zs, const double *slow, double *u, int *ierr) {
+    (void)comm;
+    *ierr = 0;
+    mceik_ctx *c = g_solve.init ? default_ctx() : nullptr;
+    const mceik_fsm_grid &g = g_solve.grid;
+    if (!c || (long long)*n != (long long)g.nx * g.ny * g.nz) {
+        printf(" eikonal3d_solve: solver not initialized or n /= nx*ny*nz\n");
+        *ierr = 1;
+        return;
+    }
+    // slowness must be positive everywhere (the reference rejects MINVAL(slow) == 0, fsm3d.f90:1802)
+    for (long long i = 0; i < *n; ++i)
+        if (slow[i] == 0.0) { printf(" eikonal3d_model: Error scattering model!\n"); *ierr = 1; return; }
+    const int fm = 0, sp[2] = {0, *nsrc};
+    int ferr = 0;
+    if (mceik_fsm_solve_batched_host(c, &g, 1, slow, 1, &fm, sp, ts, xs, ys, zs, u, nullptr, 0, nullptr, &ferr) != 0) {
+        printf(" eikonal3d_solve: %s\n", ferr ? "Error setting bcs" : mceik_last_error());
+        *ierr = 1;
+    }
+}
+
+void eikonal3d_finalize(const int *comm, int *ierr) {
+    (void)comm;
+    *ierr = 0;
+    if (!g_solve.init) {
+        printf(" eikonal3d_finalize: Solver was never initialized\n");
+        *ierr = 1;
+    }
+    g_solve = SolveState();
+}
+
+}  // extern "C"
+
+// ---- single-event full-grid searches --------------------------------------------------------
+namespace {
+template <typename T>
+int full_grid_host(int ldgrd, int ngrd, const std::vector<int> &rows, const std::vector<T> &tobs, const std::vector<T> &w0,
+                   const std::vector<T> &w1, int want_ot, T t0use, const T *test, T *t0, T *obj) {
+    mceik_ctx *c = default_ctx();
+    if (!c) return 1;
+    return guarded([&]() -> int {
+        DeviceGuard dg(c->device);
+        cudaStream_t st = c->stream;
+        const int nuse = (int)rows.size();
+        const size_t row_bytes = sizeof(T) * (size_t)ngrd, ld = (size_t)ldgrd;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+        const size_t o_test = take(sizeof(T) * ld * std::max(nuse, 1)), o_t0 = take(row_bytes), o_obj = take(row_bytes);
+        const size_t o_rows = take(sizeof(int) * std::max(nuse, 1)), o_tobs = take(sizeof(T) * std::max(nuse, 1));
+        const size_t o_w0 = take(sizeof(T) * std::max(nuse, 1)), o_w1 = take(sizeof(T) * std::max(nuse, 1));
+        char *b = static_cast<char *>(c->ws_gs_misc.ensure(off));
+        std::vector<int> compact(nuse);
+        for (int j = 0; j < nuse; ++j) {  // only the used rows travel, packed in pick order
+            compact[j] = j;
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_test + sizeof(T) * ld * j, test + ld * (size_t)rows[j], row_bytes,
+                                       cudaMemcpyHostToDevice, st));
+        }
+        if (nuse) {
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_rows, compact.data(), sizeof(int) * nuse, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_tobs, tobs.data(), sizeof(T) * nuse, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_w0, w0.data(), sizeof(T) * nuse, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_w1, w1.data(), sizeof(T) * nuse, cudaMemcpyHostToDevice, st));
+        }
+        gs::launch_full_grid<T>(ngrd, ld, nuse, reinterpret_cast<int *>(b + o_rows), reinterpret_cast<T *>(b + o_tobs),
+                                reinterpret_cast<T *>(b + o_w0), reinterpret_cast<T *>(b + o_w1), want_ot, t0use,
+                                reinterpret_cast<T *>(b + o_test), reinterpret_cast<T *>(b + o_t0),
+                                reinterpret_cast<T *>(b + o_obj), st);
+        if (t0) MCEIK_CUDA(cudaMemcpyAsync(t0, b + o_t0, row_bytes, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaMemcpyAsync(obj, b + o_obj, row_bytes, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }) == 0 ? 0 : 1;
+}
+
+template <typename T>
+int l2_gridsearch_c(const char *fcnm, int ldgrd, int ngrd, int nobs, int iwantOT, T t0use, const int *mask, const T *tobs,
+                    const T *tcorr, const T *varobs, const T *test, T *t0, T *objfn, T sqrt2i) {
+    // argument checks of locate.c:948-974 (and :1104-1130 for float)
+    if ((sizeof(T) * (size_t)ldgrd) % 64 != 0 || ldgrd < ngrd || nobs < 1 || !mask || !tobs || !varobs || !test || !t0 || !objfn) {
+        if ((sizeof(T) * (size_t)ldgrd) % 64 != 0) printf("%s: Error ldgrd must be divisible by 64\n", fcnm);
+        if (ldgrd < ngrd) printf("%s: Error ldgrd < ngrd\n", fcnm);
+        if (!mask) printf("%s: mask is null\n", fcnm);
+        if (!tobs) printf("%s: tobs is null\n", fcnm);
+        if (!varobs) printf("%s: varobs is null\n", fcnm);
+        if (!test) printf("%s: test is null\n", fcnm);
+        if (!t0) printf("%s: t0 is null\n", fcnm);
+        if (!objfn) printf("%s: objfn is null\n", fcnm);
+        return 1;
+    }
+    if ((uintptr_t)t0 % 64 || (uintptr_t)test % 64 || (uintptr_t)objfn % 64) {
+        printf("%s: Input arrays are not 64 bit aligned\n", fcnm);
+        return 1;
+    }
+    // compress the unmasked picks (locate.c:981-1013); scalar work, same fp operations in T
+    std::vector<int> rows;
+    std::vector<T> tc, wt;
+    T xnorm = (T)0;
+    for (int i = 0; i < nobs; ++i) {
+        if (mask[i] != 0) continue;
+        tc.push_back(tcorr ? tobs[i] - tcorr[i] : tobs[i]);
+        wt.push_back((T)1 / varobs[i]);
+        xnorm = xnorm + wt.back();
+        rows.push_back(i);
+    }
+    std::vector<T> w0(wt.size()), w1(wt.size());
+    for (size_t j = 0; j < wt.size(); ++j) {
+        w0[j] = wt[j] / xnorm;   // locate.c:399
+        w1[j] = wt[j] * sqrt2i;  // locate.c:500
+    }
+    if (ngrd == 0) return 0;
+    if (full_grid_host<T>(ldgrd, ngrd, rows, tc, w0, w1, iwantOT == 1, t0use, test, t0, objfn) != 0) {
+        printf("%s: %s\n", fcnm, mceik_last_error());
+        return 1;
+    }
+    return 0;
+}
+
+template <typename T>
+void gridsearch_f90(const char *fcnm, int ldgrd, int ngrd, int nobs, int iwantOT, const int *mask, const T *tobs,
+                    const T *varobs, const T *test, T *logPDF, int *ierr, T eps) {
+    *ierr = 0;
+    if (ldgrd % 64 != 0) { printf(" %s: Require arrays be 64 byte aligned\n", fcnm); *ierr = 1; return; }
+    if (ngrd > ldgrd) { printf(" %s: ngrd cannot be greater than ldgrd\n", fcnm); *ierr = 1; return; }
+    int msum = 0;
+    T vsum = (T)0;
+    for (int i = 0; i < nobs; ++i) { msum += mask[i]; vsum = vsum + varobs[i]; }
+    if (msum == nobs) { printf(" %s: No observations\n", fcnm); *ierr = 1; return; }
+    if (std::fabs(vsum - (T)0) < eps) { printf(" %s: Will be division by zero\n", fcnm); *ierr = 1; return; }
+    T xnorm = (T)0;  // sum of the variances of the unmasked picks (gridsearch.f90:431-434)
+    for (int i = 0; i < nobs; ++i)
+        if (mask[i] != 1) xnorm = xnorm + varobs[i];
+    const T sqrt2i = (T)1 / std::sqrt((T)2);
+    std::vector<int> rows;
+    std::vector<T> tc, w0, w1;
+    for (int i = 0; i < nobs; ++i) {
+        if (mask[i] == 1) continue;
+        rows.push_back(i);
+        tc.push_back(tobs[i]);
+        w0.push_back((T)1 / (varobs[i] * xnorm));  // gridsearch.f90:185
+        w1.push_back(sqrt2i / varobs[i]);          // gridsearch.f90:273
+    }
+    if (ngrd == 0) return;
+    if (full_grid_host<T>(ldgrd, ngrd, rows, tc, w0, w1, iwantOT == 1, (T)0, test, (T *)nullptr, logPDF) != 0) {
+        printf(" %s: %s\n", fcnm, mceik_last_error());
+        *ierr = 1;
+    }
+}
+
+template <typename T>
+int minloc_host(int n, const T *x) {
+    mceik_ctx *c = default_ctx();
+    if (!c || n < 1 || !x) return 0;
+    int result = 0;
+    guarded([&]() -> int {
+        DeviceGuard dg(c->device);
+        cudaStream_t st = c->stream;
+        const size_t o_s = align_up(sizeof(T) * (size_t)n), o_out = o_s + align_up(gs::minloc_scratch_bytes());
+        char *b = static_cast<char *>(c->ws_gs_misc.ensure(o_out + 256));
+        MCEIK_CUDA(cudaMemcpyAsync(b, x, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
+        gs::launch_minloc<T>(n, reinterpret_cast<T *>(b), reinterpret_cast<int *>(b + o_out), b + o_s,
+                             gs::minloc_scratch_bytes(), st);
+        MCEIK_CUDA(cudaMemcpyAsync(&result, b + o_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+    return result;
+}
+}  // namespace
+
+extern "C" {
+
+int locate_l2_gridSearch__double64(const int ldgrd, const int ngrd, const int nobs, const int iwantOT, const double t0use,
+                                   const int *mask, const double *tobs, const double *tcorr, const double *varobs,
+                                   const double *test, double *t0, double *objfn) {
+    return l2_gridsearch_c<double>("locate_l2_gridSearch__double64", ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, tcorr,
+                                   varobs, test, t0, objfn, 0.7071067811865475);
+}
+int locate_l2_gridSearch__float64(const int ldgrd, const int ngrd, const int nobs, const int iwantOT, const float t0use,
+                                  const int *mask, const float *tobs, const float *tcorr, const float *varobs,
+                                  const float *test, float *t0, float *objfn) {
+    return l2_gridsearch_c<float>("locate_l2_gridSearch__float64", ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, tcorr,
+                                  varobs, test, t0, objfn, 0.7071067811865475f);
+}
+int locate_minLocDouble64(const int n, const double *x) { return minloc_host<double>(n, x); }
+int locate_minLocFloat64(const int n, const float *x) { return minloc_host<float>(n, x); }
+
+void locate3d_gridsearch__double64(const int *ldgrd, const int *ngrd, const int *nobs, const int *iwantOT, const int *mask,
+                                   const double *tobs, const double *varobs, const double *test, double *logPDF, int *ierr) {
+    gridsearch_f90<double>("locate3d_gridsearch_double64", *ldgrd, *ngrd, *nobs, *iwantOT, mask, tobs, varobs, test, logPDF,
+                           ierr, 2.220446049250313e-16);
+}
+void locate3d_gridsearch__float64(const int *ldgrd, const int *ngrd, const int *nobs, const int *iwantOT, const int *mask,
+                                  const float *tobs, const float *varobs, const float *test, float *logPDF, int *ierr) {
+    gridsearch_f90<float>("locate3d_gridsearch_float64", *ldgrd, *ngrd, *nobs, *iwantOT, mask, tobs, varobs, test, logPDF,
+                          ierr, 1.1920929e-07f);
+}
+
+// ---- catalogue locator ----------------------------------------------------------------------
+void locate3d_initialize(const int *comm, const int *iverb, const long *tttFileID, const long *locFileID, const int *ndivx,
+                         const int *ndivy, const int *ndivz, int *ierr) {
+    (void)comm; (void)tttFileID; (void)locFileID; (void)ndivx; (void)ndivy; (void)ndivz;
+    *ierr = 0;
+    if (!default_ctx()) { printf(" locate3d_initialize: %s\n", mceik_last_error()); *ierr = 1; return; }
+    g_loc.init = true;
+    g_loc.iverb = *iverb;
+}
+
+void locate3d_gridsearch(const int *model, const int *job, const int *nobs, const int *nevents, const int *luseObs,
+                         const int *statPtr, const int *pickType, const double *statCor, const double *tori,
+                         const double *varobs, const double *tobs, double *test, double *hypo, int *ierr) {
+    (void)model; (void)test;
+    *ierr = 0;
+    mceik_ctx *c = g_loc.init ? default_ctx() : nullptr;
+    if (!c || !c->d_tables || (int)c->xlocs.size() != c->ngrd) {
+        printf(" locate3d_gridsearch: locator not initialized (tables / node coordinates missing)\n");
+        *ierr = 1;
+        return;
+    }
+    if (*job != 1 && *job != 2) {  // locate.f90:501-515
+        if (*job == 3 || *job == 5) printf(" Not yet done\n");
+        else printf(" locate_gridsearch: Invalid job\n");
+        *ierr = 1;
+        return;
+    }
+    const int ne = *nevents, no = *nobs;
+    std::vector<int> optr(ne + 1), tid((size_t)std::max(ne * no, 1)), iopt(std::max(ne, 1));
+    std::vector<double> tc((size_t)std::max(ne * no, 1)), t0(std::max(ne, 1)), obj(std::max(ne, 1));
+    for (int e = 0; e <= ne; ++e) optr[e] = e * no;
+    for (int e = 0; e < ne; ++e)
+        for (int i = 0; i < no; ++i) {
+            const size_t p = (size_t)e * no + i;  // myobs = (isrc-1)*nobs + iobs, locate.f90:394
+            tid[p] = luseObs[p] == 0 ? -1 : 2 * (statPtr[p] - 1) + (pickType[p] - 1);
+            tc[p] = tobs[p] - statCor[i];         // locate.f90:409, 453
+        }
+    if (mceik_locate_batched_host(c, *job, ne, optr.data(), tid.data(), tc.data(), varobs, tori, iopt.data(), t0.data(),
+                                  obj.data()) != 0) {
+        printf(" locate3d_gridsearch: %s\n", mceik_last_error());
+        *ierr = 1;
+        return;
+    }
+    fill_hypo(c, ne, iopt.data(), t0.data(), hypo);
+}
+
+void locate3d_finalize(void) { g_loc = LocState(); }
+
+// ---- analytic homogeneous table --------------------------------------------------------------
+int computeHomogeneousTraveltimes(const int nx, const int ny, const int nz, double x0, double y0, double z0, const double dx,
+                                  double dy, const double dz, const double xs, const double ys, double zs, const double vel,
+                                  double *ttimes) {
+    // distance * (1/vel) per node in fp64 on the device, as homog.c:605-619
+    mceik_ctx *c = default_ctx();
+    if (!c || !ttimes || nx < 1 || ny < 1 || nz < 1) return 1;
+    return guarded([&]() -> int {
+        DeviceGuard dg(c->device);
+        const size_t N = (size_t)nx * ny * nz;
+        const std::vector<double> xyzv = {xs, ys, zs, 1.0 / vel};
+        c->ws_xyzv.ensure(sizeof(double) * 4);
+        const double *d_xyzv = upload(c->ws_xyzv, 0, xyzv, c->stream);
+        double *d_t = static_cast<double *>(c->ws_u.ensure(sizeof(double) * N));
+        fsm::launch_homog_tables<double>(nx, ny, nz, x0, y0, z0, dx, dy, dz, 1, d_xyzv, d_t, N, c->stream);
+        MCEIK_CUDA(cudaMemcpyAsync(ttimes, d_t, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        MCEIK_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    }) == 0 ? 0 : 1;
+}
+
+}  // extern "C"

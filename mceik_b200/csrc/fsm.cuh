@@ -1,0 +1,88 @@
+// fsm.cuh -- batched fast-sweeping eikonal kernels: host-side launch interface.
+//
+// Reference semantics (serial path): EIKONAL3D_SETBCS fsm3d.f90:762-840, EIKONAL3D_FSM
+// fsm3d.f90:28-99, EVAL_UPDATE3D/UPDATE3D fsm3d.f90:419-546, SOLVE_HAMILTONIAN3D :648-693.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "common.cuh"
+
+namespace mceik {
+namespace fsm {
+
+constexpr int kTile = 16;                     // tile edge (nodes)
+constexpr int kTileNodes = kTile * kTile * kTile;
+constexpr int kHalo = kTile + 2;              // smem row stride of a tile with its 1-node halo
+constexpr int kHaloNodes = kHalo * kHalo * kHalo;
+constexpr int kTileLevels = 3 * kTile - 2;    // hyperplanes inside one tile
+constexpr int kMaxSlots = 4;                  // fields (sharing one slowness model) per CTA
+constexpr int kGroupThreads = 128;            // threads working on one slot
+
+// One boundary-condition record: a stencil node of one source (fsm3d.f90:810-833).
+struct BcRecord {
+    double d;       // distance source -> node (m), computed on the host exactly as :823
+    double ts;      // source time (s)
+    int node;       // flat 0-based node index
+    int collocated; // |d| < 1e-10 -> assign instead of min (:825-829)
+};
+
+// Static description of the tile decomposition of an (nx,ny,nz) grid.
+struct TilePlan {
+    int nx = 0, ny = 0, nz = 0;
+    int ntx = 0, nty = 0, ntz = 0, ntiles = 0, ntlevels = 0;
+    DevBuf tile_order;  // int[ntiles]: I | J<<10 | K<<20, sorted by I+J+K
+    DevBuf tlevel_ptr;  // int[ntlevels+1]
+    DevBuf lvl_nodes;   // uint16[kTileNodes]: a | b<<4 | c<<8 sorted by a+b+c, then c, then b
+    std::vector<int> h_tlevel_ptr;
+    void build(int nx_, int ny_, int nz_, cudaStream_t st);
+    void release();
+};
+
+// Arguments of one launch of the tile-wavefront sweep kernel (= one FSM iteration = 8 sweeps).
+struct SweepArgs {
+    int nx, ny, nz;
+    int ntx, nty, ntz, ntiles, ntlevels;
+    int ngroups, nslots;
+    double h, tol;
+    const int *group_fields;  // [ngroups][kMaxSlots] field index or -1
+    const int *group_model;   // [ngroups]
+    const double *slow;       // [nmodels][N]
+    double *u;                // [nfields][N]
+    double *u0;               // [nfields][N] values at the start of the iteration
+    const int *tile_order;
+    const int *tlevel_ptr;
+    const uint16_t *lvl_nodes;
+    int *done;                  // [ngroups][ntiles] sweeps completed per tile, zeroed per launch
+    int *queue;                 // [1] ticket counter, zeroed per launch
+    unsigned long long *nonconv; // [nfields] nodes with !(|u0-u| < tol), zeroed per launch
+    const int *bc_ptr;          // [nfields+1] CSR into bc_tile / bc_local
+    const int *bc_tile;         // tile id of each (unique) boundary-condition node
+    const uint16_t *bc_local;   // i | j<<4 | k<<8 inside that tile
+};
+
+void launch_fill(double *d_u, size_t n, double value, cudaStream_t st);
+// One thread per field applies its BcRecords in source order.
+void launch_apply_bcs(int nfields, size_t n, const int *d_field_model, const int *d_rec_ptr,
+                      const BcRecord *d_recs, const double *d_slow, double *d_u, cudaStream_t st);
+void launch_iteration_tiles(const SweepArgs &a, cudaStream_t st);
+size_t tiles_smem_bytes(int nslots);
+// Debug / cross-check path: one launch per hyperplane, global memory only.
+void launch_iteration_levels(int nx, int ny, int nz, double h, int nfields, const int *d_active_fields,
+                             const int *d_field_model, const double *d_slow, const uint8_t *d_lupd,
+                             double *d_u, cudaStream_t st);
+// u0 = u and count !(|u0-u| < tol) per field (used by the levels path; fsm3d.f90:86-90).
+void launch_convergence(size_t n, int nfields, const int *d_active_fields, double tol, const double *d_u,
+                        double *d_u0, unsigned long long *d_nonconv, cudaStream_t st);
+void launch_mark_bcs(int nrec, const int *d_rec_field, const int *d_rec_node, size_t n, uint8_t *d_lupd,
+                     cudaStream_t st);
+// fp64 field -> fp32 table (fsm3d.f90:1870-1872, homog.c:624-635)
+void launch_pack_tables(int nfields, size_t n, size_t ldtab, const double *d_u, float *d_tables,
+                        cudaStream_t st);
+// analytic homogeneous field(s): OutT = float (locator tables) or double (homog.c:594-621 as is)
+template <typename OutT>
+void launch_homog_tables(int nx, int ny, int nz, double x0, double y0, double z0, double dx, double dy,
+                         double dz, int nstations, const double *d_xyzv, OutT *d_tables, size_t ldtab,
+                         cudaStream_t st);
+
+}  // namespace fsm
+}  // namespace mceik

@@ -1,0 +1,393 @@
+// gs.cu -- L2 travel-time-table grid search for sm_100a.
+//
+// Per event e and grid node g (reference: locate.c:923-1047, stack kernels :388-567):
+//     t0[g]  = sum_i (w_i/sum w) * (tobs_i - T_i[g])                 w_i = 1/var_i
+//     obj[g] = sum_i ( (w_i/sqrt2) * (tobs_i - (T_i[g] + t0[g])) )^2
+//     iopt   = first index of the strict minimum of obj               (locate.c:811-830)
+// accumulated over the used picks in catalogue order, with separate IEEE multiply and add (the
+// reference build has no FMA), which is what makes the located index bit-exact.
+//
+// The reference streams every table twice per event and read-modify-writes t0/obj grids per
+// pick.  Here nothing grid-sized is ever written: a CTA keeps t0 and obj of 8 events x 512
+// nodes in registers, walks the picks once per pass with the table row loaded once for all 8
+// events, reduces (obj, node, t0) with warp shuffles, and carries a running optimum across the
+// chunks of the grid it owns.  fp32 tables are promoted to fp64 on load (locate.f90:414,459).
+#include <algorithm>
+#include <climits>
+#include "gs.cuh"
+
+namespace mceik {
+namespace gs {
+
+// literal of locate.c:496; note it rounds to 0x3FE6A09E667F3BCC, one ulp below M_SQRT1_2
+#define MCEIK_SQRT2I 0.7071067811865475
+
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// ------------------------------------------------------------------------------------------
+__global__ void prepare_kernel(int nevents, const int *__restrict__ obs_ptr, const int *__restrict__ table_id,
+                               const double *__restrict__ varobs, double *__restrict__ w_t0,
+                               double *__restrict__ w_obj, int *__restrict__ nuse) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nevents) return;
+    const int beg = obs_ptr[e], end = obs_ptr[e + 1];
+    double xnorm = 0.0;
+    int n = 0;
+    for (int p = beg; p < end; ++p)
+        if (table_id[p] >= 0) {
+            xnorm = __dadd_rn(xnorm, __ddiv_rn(1.0, varobs[p]));  // locate.c:993-994
+            ++n;
+        }
+    for (int p = beg; p < end; ++p) {
+        double a = 0.0, b = 0.0;
+        if (table_id[p] >= 0) {
+            const double wt = __ddiv_rn(1.0, varobs[p]);
+            a = __ddiv_rn(wt, xnorm);         // locate.c:399
+            b = __dmul_rn(wt, MCEIK_SQRT2I);  // locate.c:500
+        }
+        w_t0[p] = a;
+        w_obj[p] = b;
+    }
+    nuse[e] = n;
+}
+
+void launch_prepare(int nevents, const int *d_obs_ptr, const int *d_table_id, const double *d_varobs,
+                    double *d_w_t0, double *d_w_obj, int *d_nuse, cudaStream_t st) {
+    if (nevents == 0) return;
+    prepare_kernel<<<(nevents + 127) / 128, 128, 0, st>>>(nevents, d_obs_ptr, d_table_id, d_varobs, d_w_t0,
+                                                          d_w_obj, d_nuse);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// (obj, node, t0) "less": smaller objective first, then smaller node index; NaN never wins.
+__device__ __forceinline__ bool better(double v, int i, double bv, int bi) {
+    return (v < bv) || (v == bv && i < bi);
+}
+
+template <int EB, int R>
+__global__ void __launch_bounds__(kThreads, 2) locate_kernel(const LocateArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int P = a.maxpicks;
+    double *s_tobs = reinterpret_cast<double *>(smem);  // [P][EB]
+    double *s_w0 = s_tobs + (size_t)EB * P;
+    double *s_w1 = s_w0 + (size_t)EB * P;
+    int *s_id = reinterpret_cast<int *>(s_w1 + (size_t)EB * P);
+    __shared__ double r_val[kThreads / 32][EB], r_t0[kThreads / 32][EB];
+    __shared__ int r_idx[kThreads / 32][EB];
+    __shared__ int s_nan0[EB];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int e0 = blockIdx.y * EB;
+
+    for (int q = tid; q < EB * P; q += kThreads) {
+        const int j = q / EB, e = q - j * EB, ev = e0 + e;
+        int id = -1;
+        double to = 0.0, w0 = 0.0, w1 = 0.0;
+        if (ev < a.nevents) {
+            const int beg = a.obs_ptr[ev];
+            if (j < a.obs_ptr[ev + 1] - beg) {
+                id = a.table_id[beg + j];
+                to = a.tobs_cor[beg + j];
+                w0 = a.w_t0[beg + j];
+                w1 = a.w_obj[beg + j];
+            }
+        }
+        s_id[q] = id; s_tobs[q] = to; s_w0[q] = w0; s_w1[q] = w1;
+    }
+    if (tid < EB) s_nan0[tid] = 0;
+    __syncthreads();
+
+    double tfix[EB];
+#pragma unroll
+    for (int e = 0; e < EB; ++e) tfix[e] = (a.job == 2 || e0 + e >= a.nevents) ? 0.0 : a.tori[e0 + e];
+
+    // running optimum of event `tid` (threads 0..EB-1 only)
+    double best_val = d_inf(), best_t0 = 0.0;
+    int best_idx = INT_MAX;
+
+    const int nchunks = (a.ngrd + kChunk - 1) / kChunk;
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        int g[R], gl[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            g[r] = chunk * kChunk + r * kThreads + tid;
+            gl[r] = min(g[r], a.ngrd - 1);
+        }
+        double t0[EB][R], obj[EB][R];
+#pragma unroll
+        for (int e = 0; e < EB; ++e)
+#pragma unroll
+            for (int r = 0; r < R; ++r) { t0[e][r] = tfix[e]; obj[e][r] = 0.0; }
+
+#pragma unroll 1
+        for (int pass = (a.job == 2 ? 0 : 1); pass < 2; ++pass) {
+            const double *s_w = pass == 0 ? s_w0 : s_w1;
+            // table row of the first used pick of slot j, loaded one slot ahead
+            double Tn[R];
+            int idn = -1;
+#pragma unroll
+            for (int e = EB - 1; e >= 0; --e) if (s_id[e] >= 0) idn = s_id[e];
+            if (idn >= 0) {
+                const float *row = a.tables + (size_t)idn * a.ldgrd;
+#pragma unroll
+                for (int r = 0; r < R; ++r) Tn[r] = (double)__ldg(row + gl[r]);
+            }
+#pragma unroll 1
+            for (int j = 0; j < P; ++j) {
+                double T[R];
+                int cur = idn;
+#pragma unroll
+                for (int r = 0; r < R; ++r) T[r] = Tn[r];
+                idn = -1;
+                if (j + 1 < P) {
+#pragma unroll
+                    for (int e = EB - 1; e >= 0; --e) if (s_id[(j + 1) * EB + e] >= 0) idn = s_id[(j + 1) * EB + e];
+                    if (idn >= 0) {
+                        const float *row = a.tables + (size_t)idn * a.ldgrd;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) Tn[r] = (double)__ldg(row + gl[r]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < EB; ++e) {
+                    const int id = s_id[j * EB + e];
+                    if (id >= 0) {  // uniform across the CTA
+                        if (id != cur) {
+                            cur = id;
+                            const float *row = a.tables + (size_t)id * a.ldgrd;
+#pragma unroll
+                            for (int r = 0; r < R; ++r) T[r] = (double)__ldg(row + gl[r]);
+                        }
+                        const double to = s_tobs[j * EB + e], w = s_w[j * EB + e];
+                        if (pass == 0) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r)  // locate.c:409
+                                t0[e][r] = __dadd_rn(t0[e][r], __dmul_rn(w, __dsub_rn(to, T[r])));
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < R; ++r) {  // locate.c:511-512
+                                const double res = __dmul_rn(w, __dsub_rn(to, __dadd_rn(T[r], t0[e][r])));
+                                obj[e][r] = __dadd_rn(obj[e][r], __dmul_rn(res, res));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- optimum of this chunk per event
+        if (chunk == 0 && tid == 0) {
+#pragma unroll
+            for (int e = 0; e < EB; ++e) if (obj[e][0] != obj[e][0]) s_nan0[e] = 1;
+        }
+#pragma unroll
+        for (int e = 0; e < EB; ++e) {
+            double bv = d_inf(), bt = 0.0;
+            int bi = INT_MAX;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (g[r] < a.ngrd && better(obj[e][r], g[r], bv, bi)) { bv = obj[e][r]; bi = g[r]; bt = t0[e][r]; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+                const double ot = __shfl_down_sync(0xffffffffu, bt, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+            }
+            if (lane == 0) { r_val[warp][e] = bv; r_t0[warp][e] = bt; r_idx[warp][e] = bi; }
+        }
+        __syncthreads();
+        if (tid < EB) {
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w)
+                if (better(r_val[w][tid], r_idx[w][tid], best_val, best_idx)) {
+                    best_val = r_val[w][tid]; best_idx = r_idx[w][tid]; best_t0 = r_t0[w][tid];
+                }
+        }
+        __syncthreads();
+    }
+
+    if (tid < EB && e0 + tid < a.nevents) {
+        Partial p;
+        p.val = best_val; p.t0 = best_t0; p.idx = best_idx; p.nan0 = s_nan0[tid];
+        a.partials[(size_t)(e0 + tid) * a.nlanes + blockIdx.x] = p;
+    }
+}
+
+size_t locate_smem_bytes(int maxpicks) {
+    return (size_t)kEventsPerBlock * (size_t)std::max(maxpicks, 1) * (3 * sizeof(double) + sizeof(int));
+}
+
+int locate_lanes(int nevents, int ngrd) {
+    const int nblocks = (nevents + kEventsPerBlock - 1) / kEventsPerBlock;
+    const int nchunks = (ngrd + kChunk - 1) / kChunk;
+    const int target = 148 * 2 * 2;  // two CTAs per SM, two waves
+    int lanes = (target + nblocks - 1) / std::max(nblocks, 1);
+    return std::max(1, std::min(lanes, nchunks));
+}
+
+void launch_locate(const LocateArgs &a, cudaStream_t st) {
+    if (a.nevents == 0) return;
+    const size_t smem = locate_smem_bytes(a.maxpicks);
+    if (smem > 200 * 1024) throw CudaError("too many picks per event for the locate kernel (limit ~900)");
+    auto kern = locate_kernel<kEventsPerBlock, kPointsPerThread>;
+    MCEIK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nblocks = (a.nevents + kEventsPerBlock - 1) / kEventsPerBlock;
+    if (nblocks > 65535) throw CudaError("too many events per call (limit 524280)");
+    dim3 grid(a.nlanes, nblocks);
+    kern<<<grid, kThreads, smem, st>>>(a);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// one warp per event merges the lane partials
+__global__ void finalize_kernel(int nevents, int nlanes, const Partial *__restrict__ partials,
+                                const int *__restrict__ nuse, int *__restrict__ iopt, double *__restrict__ t0opt,
+                                double *__restrict__ objopt) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= nevents) return;
+    double bv = d_inf(), bt = 0.0;
+    int bi = INT_MAX, nan0 = 0;
+    for (int l = lane; l < nlanes; l += 32) {
+        const Partial p = partials[(size_t)e * nlanes + l];
+        nan0 |= p.nan0;
+        if (better(p.val, p.idx, bv, bi)) { bv = p.val; bi = p.idx; bt = p.t0; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const double ot = __shfl_down_sync(0xffffffffu, bt, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        nan0 |= __shfl_down_sync(0xffffffffu, nan0, off);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bt = ot; }
+    }
+    if (lane == 0) {
+        if (nuse[e] == 0) {           // no usable pick: flagged, nothing located
+            iopt[e] = -1; t0opt[e] = 0.0; objopt[e] = 0.0;
+        } else if (nan0 || bi == INT_MAX) {  // NaN at node 0 is sticky in locate.c:821-828 -> index 0
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            iopt[e] = 0; t0opt[e] = qnan; objopt[e] = qnan;
+        } else {
+            iopt[e] = bi; t0opt[e] = bt; objopt[e] = bv;
+        }
+    }
+}
+
+void launch_finalize(int nevents, int nlanes, const Partial *d_partials, const int *d_nuse, int *d_iopt,
+                     double *d_t0opt, double *d_objopt, cudaStream_t st) {
+    if (nevents == 0) return;
+    const int threads = 128;
+    const int blocks = (int)(((size_t)nevents * 32 + threads - 1) / threads);
+    finalize_kernel<<<blocks, threads, 0, st>>>(nevents, nlanes, d_partials, d_nuse, d_iopt, d_t0opt, d_objopt);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// Single event, full-grid outputs (the legacy per-call contract).
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+};
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+};
+
+template <typename T>
+__global__ void full_grid_kernel(int ngrd, size_t ldgrd, int nuse, const int *__restrict__ row, const T *__restrict__ tobs,
+                                 const T *__restrict__ w_t0, const T *__restrict__ w_obj, int want_ot, T t0use,
+                                 const T *__restrict__ test, T *__restrict__ t0out, T *__restrict__ objout) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngrd) return;
+    T t0 = want_ot ? (T)0 : t0use;
+    if (want_ot)
+        for (int j = 0; j < nuse; ++j)  // locate.c:407-410 / gridsearch.f90:189-191
+            t0 = Ar<T>::add(t0, Ar<T>::mul(w_t0[j], Ar<T>::sub(tobs[j], __ldg(test + (size_t)row[j] * ldgrd + g))));
+    T obj = (T)0;
+    for (int j = 0; j < nuse; ++j) {    // locate.c:509-513 / gridsearch.f90:277-280
+        const T res = Ar<T>::mul(w_obj[j], Ar<T>::sub(tobs[j], Ar<T>::add(__ldg(test + (size_t)row[j] * ldgrd + g), t0)));
+        obj = Ar<T>::add(obj, Ar<T>::mul(res, res));
+    }
+    t0out[g] = t0;
+    objout[g] = obj;
+}
+
+template <typename T>
+void launch_full_grid(int ngrd, size_t ldgrd, int nuse, const int *d_row, const T *d_tobs, const T *d_w_t0,
+                      const T *d_w_obj, int want_ot, T t0use, const T *d_test, T *d_t0, T *d_obj, cudaStream_t st) {
+    if (ngrd == 0) return;
+    full_grid_kernel<T><<<(ngrd + 255) / 256, 256, 0, st>>>(ngrd, ldgrd, nuse, d_row, d_tobs, d_w_t0, d_w_obj, want_ot,
+                                                            t0use, d_test, d_t0, d_obj);
+    MCEIK_LAUNCH_CHECK();
+}
+template void launch_full_grid<double>(int, size_t, int, const int *, const double *, const double *, const double *,
+                                       int, double, const double *, double *, double *, cudaStream_t);
+template void launch_full_grid<float>(int, size_t, int, const int *, const float *, const float *, const float *, int,
+                                      float, const float *, float *, float *, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// locate_minLoc{Double64,Float64} (locate.c:811-851)
+// ------------------------------------------------------------------------------------------
+constexpr int kMinlocBlocks = 148 * 4;
+struct MinPart { double v; int i; int pad; };
+size_t minloc_scratch_bytes() { return sizeof(MinPart) * kMinlocBlocks; }
+
+template <typename T>
+__global__ void minloc_stage1(int n, const T *__restrict__ x, MinPart *__restrict__ parts) {
+    double bv = d_inf();
+    int bi = INT_MAX;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double v = (double)x[i];  // float -> double is exact and order preserving
+        if (better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) if (better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        parts[blockIdx.x].v = bv; parts[blockIdx.x].i = bi;
+    }
+}
+template <typename T>
+__global__ void minloc_stage2(int nparts, const MinPart *__restrict__ parts, const T *__restrict__ x, int *__restrict__ out) {
+    double bv = d_inf();
+    int bi = INT_MAX;
+    for (int p = threadIdx.x; p < nparts; p += 32)
+        if (better(parts[p].v, parts[p].i, bv, bi)) { bv = parts[p].v; bi = parts[p].i; }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+        const T x0 = x[0];
+        out[0] = (x0 != x0 || bi == INT_MAX) ? 0 : bi;  // a NaN at x[0] is sticky in the reference scan
+    }
+}
+
+template <typename T>
+void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (scratch_bytes < minloc_scratch_bytes()) throw CudaError("minloc scratch too small");
+    MinPart *parts = reinterpret_cast<MinPart *>(d_scratch);
+    const int blocks = std::max(1, std::min(kMinlocBlocks, (n + 255) / 256));
+    minloc_stage1<T><<<blocks, 256, 0, st>>>(n, d_x, parts);
+    MCEIK_LAUNCH_CHECK();
+    minloc_stage2<T><<<1, 32, 0, st>>>(blocks, parts, d_x, d_out);
+    MCEIK_LAUNCH_CHECK();
+}
+template void launch_minloc<double>(int, const double *, int *, void *, size_t, cudaStream_t);
+template void launch_minloc<float>(int, const float *, int *, void *, size_t, cudaStream_t);
+
+}  // namespace gs
+}  // namespace mceik

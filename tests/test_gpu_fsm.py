@@ -1,0 +1,146 @@
+"""GPU parity tests of the eikonal path: CUDA (through the C ABI) vs the CPU oracle, bit for bit.
+
+Bit-exactness holds because updates inside one hyperplane are order independent
+and neither side fuses multiply-adds.  Tolerance in these tests: 0 ulp (np.array_equal).
+"""
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_fields(nx, ny, nz, h, slow, fmodel, xs, ys, zs, ts, tol, maxit):
+    out, its = [], []
+    for f in range(len(fmodel)):
+        u, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow[fmodel[f]], ts[f], xs[f], ys[f], zs[f], tol=tol, maxit=maxit)
+        assert ierr == 0
+        out.append(u)
+        its.append(it)
+    return np.stack(out), np.array(its)
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_xfsm3d_case_matches_oracle(gpu_ctx, algo):
+    """The reference's own driver case (fsm3d.f90:2085-2100): 70x80x90, h=100, v=5000, centre source."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 70, 80, 90, 100.0
+    slow = np.full(nx * ny * nz, 1.0 / 5000.0)
+    xs, ys, zs = h * nx / 2, h * ny / 2, h * nz / 2
+    ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs, ys, zs, tol=1e-7, maxit=5)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-7, maxit=5, algo=algo)
+    u, _, iters, ferr = sol.solve_host(slow[None], [0], [0.0], [xs], [ys], [zs])
+    assert ferr[0] == 0 and iters[0] == it == 2
+    assert np.array_equal(u[0], ref)
+    assert sol.node_updates == nx * ny * nz * 8 * it
+
+
+@pytest.mark.parametrize("shape", [(37, 50, 21), (16, 16, 16), (5, 70, 3), (33, 17, 48)])
+def test_random_model_two_sources_bit_exact(gpu_ctx, shape):
+    """Heterogeneous random slowness, partial tiles, two sources seeding one field."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz = shape
+    h = 100.0
+    slow = cases.random_slowness(nx * ny * nz, seed=7)
+    ts = np.array([0.0, 0.3])
+    xs = np.array([h * nx * 0.37, h * nx * 0.8])
+    ys = np.array([h * ny * 0.61, h * 2.0])
+    zs = np.array([h * nz * 0.45, h * (nz - 2.5)])
+    ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, ts, xs, ys, zs, tol=1e-6, maxit=20)
+    assert ierr == 0
+    for algo in (0, 1):
+        sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20, algo=algo)
+        u, _, iters, ferr = sol.solve_host(slow[None], [0], ts, xs, ys, zs, src_ptr=[0, 2])
+        assert ferr[0] == 0 and iters[0] == it
+        assert np.array_equal(u[0], ref), f"algo {algo}: {np.count_nonzero(u[0] != ref)} nodes differ"
+
+
+def test_batched_fields_two_models(gpu_ctx):
+    """7 fields over 2 slowness models (groups of 4, 1 and 2 slots), each equal to its own serial solve;
+    fields converge after different iteration counts."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 48, 40, 56, 250.0
+    n = nx * ny * nz
+    slow = np.stack([cases.checkerboard_slowness(nx, ny, nz, cell=8), cases.random_slowness(n, 3)])
+    fmodel = np.array([0, 1, 0, 0, 1, 0, 0], dtype=np.int32)
+    xs, ys, zs = cases.interior_sources(7, nx, ny, nz, h, seed=11)
+    ts = np.linspace(0.0, 1.0, 7)
+    ref, its = _oracle_fields(nx, ny, nz, h, slow, fmodel, xs, ys, zs, ts, 1e-6, 20)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
+    u, tab, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, want_tables=True)
+    assert not ferr.any()
+    assert np.array_equal(iters, its)
+    assert np.array_equal(u, ref)
+    assert np.array_equal(tab, ref.astype(np.float32))  # SNGL(u), fsm3d.f90:1870-1872
+    assert sol.node_updates == int(n * 8 * its.sum())
+
+
+def test_c2_layered_128_bit_exact(gpu_ctx):
+    """BASELINE config 2: 128^3, 1-D layered model, one station."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx = ny = nz = 128
+    h = 1000.0
+    slow = cases.layered_slowness(nx, ny, nz)
+    xs, ys, zs = cases.interior_sources(1, nx, ny, nz, h, seed=1)
+    ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs[0], ys[0], zs[0])
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h)
+    u, _, iters, ferr = sol.solve_host(slow[None], [0], [0.0], xs, ys, zs)
+    assert iters[0] == it and np.array_equal(u[0], ref)
+
+
+def test_maxit_cap_and_edge_sources(gpu_ctx):
+    """maxit smaller than needed is not an error; a source on node 1 / outside the grid gives ierr=1
+    for that field only (EIKONAL_INIT_GRID quirk, fsm3d.f90:736-751); a source on node nx-1 keeps two nodes."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 24, 20, 18, 50.0
+    n = nx * ny * nz
+    slow = cases.random_slowness(n, 5)
+    xs = np.array([h * 11.3, 0.0, h * (nx - 2), -5.0])
+    ys = np.array([h * 7.7, h * 5.5, h * 9.0, h * 3.0])
+    zs = np.array([h * 8.1, h * 5.5, h * 9.0, h * 3.0])
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-9, maxit=1)
+    u, _, iters, ferr = sol.solve_host(slow[None], [0, 0, 0, 0], np.zeros(4), xs, ys, zs)
+    assert list(ferr) == [0, 1, 0, 1]
+    for f in (0, 2):
+        ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs[f], ys[f], zs[f], tol=1e-9, maxit=1)
+        assert ierr == 0 and it == 1 and iters[f] == 1
+        assert np.array_equal(u[f], ref)
+    _, ierr, _ = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs[1], ys[1], zs[1])
+    assert ierr == 1
+
+
+def test_serial_driver_lifecycle(gpu_ctx):
+    """Drop-in eikonal3d_serial_driver: job 1/2/3, double init and solve-before-init give ierr=1
+    (fsm3d.f90:1993-2013); eikonal3d_initialize/solve/finalize give the same field."""
+    from mceik_b200 import eikonal as E
+    nx, ny, nz, h = 30, 26, 22, 200.0
+    n = nx * ny * nz
+    slow = cases.random_slowness(n, 9)
+    xs, ys, zs = cases.interior_sources(1, nx, ny, nz, h, seed=2)
+    u = np.zeros(n)
+    args = (0, 20, 1, nx, ny, nz, 1e-6, h, 0.0, 0.0, 0.0, [0.25], xs, ys, zs, slow, u)
+    assert E.eikonal3d_serial_driver(2, *args) == 1
+    assert E.eikonal3d_serial_driver(1, *args) == 0
+    assert E.eikonal3d_serial_driver(1, *args) == 1
+    assert E.eikonal3d_serial_driver(2, *args) == 0
+    assert E.eikonal3d_serial_driver(3, *args) == 0
+    ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, 0.25, xs[0], ys[0], zs[0])
+    assert np.array_equal(u, ref)
+    u2 = np.zeros(n)
+    assert E.eikonal3d_solve(0, 1, n, [0.25], xs, ys, zs, slow, u2) == 1  # before initialize
+    assert E.eikonal3d_initialize(0, 0, nx, ny, nz, 2, 2, 2, 1, 20, 0.0, 0.0, 0.0, h, 1e-6) == 0
+    assert E.eikonal3d_solve(0, 1, n, [0.25], xs, ys, zs, slow, u2) == 0
+    assert E.eikonal3d_finalize(0) == 0
+    assert E.eikonal3d_finalize(0) == 1
+    assert np.array_equal(u2, ref)
+
+
+def test_homogeneous_tables(gpu_ctx):
+    """computeHomogeneousTraveltimes drop-in vs the oracle restatement of homog.c:594-621."""
+    from mceik_b200 import eikonal as E
+    nx, ny, nz = 32, 29, 26
+    t = E.compute_homogeneous_traveltimes(nx, ny, nz, 0.0, 0.0, 0.0, 1000.0, 1000.0, 1000.0, 7000.0, 12000.0, 25000.0, 2000.0)
+    ref = O.homogeneous_traveltimes(nx, ny, nz, 0.0, 0.0, 0.0, 1000.0, 1000.0, 1000.0, 7000.0, 12000.0, 25000.0, 2000.0)
+    assert np.array_equal(t, ref)

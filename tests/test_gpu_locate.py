@@ -1,0 +1,228 @@
+"""GPU parity tests of the L2 grid search: CUDA (through the C ABI) vs the reference's own
+locate.c (oracle/_ref) and the oracle restatements.  Located indices must be identical; t0 and
+objective are compared bit for bit (tolerance 0) because both sides do the same IEEE operations
+in the same order."""
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as O
+import refcases
+
+pytestmark = pytest.mark.gpu
+
+
+def test_locate_c_main_known_answer_double(gpu_ctx):
+    """locate.c main: index 107312, t0 = 4.0 (locate.c:118-182), and grids equal the reference's own code."""
+    from mceik_b200 import locate as L
+    c = refcases.locate_c_main_case()
+    t0 = L.aligned_empty(c["ngrd"], np.float64)
+    obj = L.aligned_empty(c["ngrd"], np.float64)
+    rc = L.locate_l2_gridSearch__double64(c["ldgrd"], c["ngrd"], c["nobs"], 1, c["t0use"], c["mask"], c["tobs"], c["tcorr"],
+                                          c["varobs"], c["test"], t0, obj)
+    assert rc == 0
+    iopt = L.locate_minLocDouble64(c["ngrd"], obj)
+    assert iopt == c["true_index"] == 107312
+    assert abs(t0[iopt] - 4.0) < 1e-9
+    use_ref = O.ref() is not None
+    rc2, t0r, objr = O.l2_gridsearch(c["ldgrd"], c["ngrd"], c["nobs"], 1, c["t0use"], c["mask"], c["tobs"], c["tcorr"],
+                                     c["varobs"], c["test"], np.float64, use_ref=use_ref)
+    assert rc2 == 0 and np.array_equal(t0, t0r) and np.array_equal(obj, objr)
+    assert iopt == O.minloc(objr, use_ref=use_ref)
+
+
+def test_locate_c_main_known_answer_float(gpu_ctx):
+    from mceik_b200 import locate as L
+    c = refcases.locate_c_main_case()
+    n, ld, nobs = c["ngrd"], c["ldgrd"], c["nobs"]
+    test4 = L.aligned_empty(nobs * ld, np.float32)
+    test4[:] = c["test"].astype(np.float32)
+    tobs4, var4, tc4 = c["tobs"].astype(np.float32), c["varobs"].astype(np.float32), np.zeros(nobs, np.float32)
+    t0 = L.aligned_empty(n, np.float32)
+    obj = L.aligned_empty(n, np.float32)
+    assert L.locate_l2_gridSearch__float64(ld, n, nobs, 1, 4.0, c["mask"], tobs4, tc4, var4, test4, t0, obj) == 0
+    assert L.locate_minLocFloat64(n, obj) == 107312
+    use_ref = O.ref() is not None
+    rc2, t0r, objr = O.l2_gridsearch(ld, n, nobs, 1, 4.0, c["mask"], tobs4, tc4, var4, test4, np.float32, use_ref=use_ref)
+    assert rc2 == 0 and np.array_equal(t0, t0r) and np.array_equal(obj, objr)
+
+
+def test_l2_masks_tcorr_fixed_t0_and_errors(gpu_ctx):
+    """Masked picks, static corrections, iwantOT != 1, NULL tcorr and the argument errors of locate.c:948-974."""
+    from mceik_b200 import locate as L
+    rng = np.random.default_rng(3)
+    nx, ny, nz, nobs = 23, 19, 11, 9
+    n = nx * ny * nz
+    ld = n + 64 - n % 64
+    test = L.aligned_empty(nobs * ld, np.float64)
+    for i in range(nobs):
+        test[i * ld: i * ld + n] = refcases._table(nx, ny, nz, 500.0, 500.0, 500.0, *(rng.random(3) * 5000.0))
+    tobs = rng.random(nobs) * 3 + 1
+    tcorr = rng.normal(0, 0.05, nobs)
+    var = rng.uniform(0.1, 0.9, nobs)
+    mask = (rng.random(nobs) < 0.3).astype(np.int32)
+    mask[0] = 0
+    for want, tc in ((1, tcorr), (0, tcorr), (1, None)):
+        t0 = L.aligned_empty(n, np.float64)
+        obj = L.aligned_empty(n, np.float64)
+        assert L.locate_l2_gridSearch__double64(ld, n, nobs, want, 2.5, mask, tobs, tc, var, test, t0, obj) == 0
+        rc, t0r, objr = O.l2_gridsearch(ld, n, nobs, want, 2.5, mask, tobs, tc, var, test, np.float64, use_ref=O.ref() is not None)
+        assert rc == 0 and np.array_equal(t0, t0r) and np.array_equal(obj, objr)
+        assert L.locate_minLocDouble64(n, obj) == O.minloc(objr)
+    t0 = L.aligned_empty(n, np.float64)
+    obj = L.aligned_empty(n, np.float64)
+    assert L.locate_l2_gridSearch__double64(ld + 1, n, nobs, 1, 0.0, mask, tobs, tcorr, var, test, t0, obj) == 1
+    assert L.locate_l2_gridSearch__double64(64, n, nobs, 1, 0.0, mask, tobs, tcorr, var, test, t0, obj) == 1
+    assert L.locate_l2_gridSearch__double64(ld, n, 0, 1, 0.0, mask, tobs, tcorr, var, test, t0, obj) == 1
+    assert L.locate_l2_gridSearch__double64(ld, n, nobs, 1, 0.0, None, tobs, tcorr, var, test, t0, obj) == 1
+    assert L.locate_l2_gridSearch__double64(ld, n, nobs, 1, 0.0, mask, tobs, tcorr, var, test[1:], t0, obj) == 1  # unaligned
+
+
+def test_minloc_ties_and_nan(gpu_ctx):
+    from mceik_b200 import locate as L
+    x = np.array([3.0, 1.0, 2.0, 1.0, 1.0, 5.0] * 1000)
+    assert L.locate_minLocDouble64(x.size, x) == O.minloc(x) == 1
+    x[4001] = -7.0
+    x[5000] = -7.0
+    assert L.locate_minLocDouble64(x.size, x) == O.minloc(x) == 4001
+    y = x.astype(np.float32)
+    assert L.locate_minLocFloat64(y.size, y) == O.minloc(y) == 4001
+    x[0] = np.nan  # sticky in the reference scan (locate.c:821-828)
+    assert L.locate_minLocDouble64(x.size, x) == O.minloc(x) == 0
+    z = np.full(100, np.inf)
+    assert L.locate_minLocDouble64(z.size, z) == O.minloc(z) == 0
+
+
+def test_gridsearch_f90_known_answer(gpu_ctx):
+    """gridsearch.f90 program: 1-based index 21124, t0 = 4 by construction; fp64 and fp32 grids equal the oracle."""
+    from mceik_b200 import locate as L
+    c = refcases.gridsearch_f90_case()
+    n, ld, nobs = c["ngrd"], c["ldgrd"], c["nobs"]
+    pdf = L.aligned_empty(n, np.float64)
+    assert L.locate3d_gridsearch__double64(ld, n, nobs, 1, c["mask"], c["tobs"], c["varobs"], c["test"], pdf) == 0
+    ierr, ref, t0r = O.gridsearch_f90(ld, n, nobs, 1, c["mask"], c["tobs"], c["varobs"], c["test"], np.float64)
+    assert ierr == 0 and np.array_equal(pdf, ref)
+    iopt = L.locate_minLocDouble64(n, pdf)
+    assert iopt + 1 == c["true_index_1based"] == 21124
+    assert abs(t0r[iopt] - 4.0) < 1e-9
+    test4 = L.aligned_empty(nobs * ld, np.float32)
+    test4[:] = c["test"].astype(np.float32)
+    tobs4, var4 = c["tobs"].astype(np.float32), c["varobs"].astype(np.float32)
+    pdf4 = L.aligned_empty(n, np.float32)
+    assert L.locate3d_gridsearch__float64(ld, n, nobs, 1, c["mask"], tobs4, var4, test4, pdf4) == 0
+    ierr, ref4, _ = O.gridsearch_f90(ld, n, nobs, 1, c["mask"], tobs4, var4, test4, np.float32)
+    assert ierr == 0 and np.array_equal(pdf4, ref4)
+    # non-unit variances + a masked pick + the error returns of gridsearch.f90:404-424
+    var = np.linspace(0.2, 1.5, nobs)
+    mask = c["mask"].copy()
+    mask[3] = 1
+    assert L.locate3d_gridsearch__double64(ld, n, nobs, 1, mask, c["tobs"], var, c["test"], pdf) == 0
+    ierr, ref, _ = O.gridsearch_f90(ld, n, nobs, 1, mask, c["tobs"], var, c["test"], np.float64)
+    assert np.array_equal(pdf, ref)
+    assert L.locate3d_gridsearch__double64(ld, n, nobs, 0, mask, c["tobs"], var, c["test"], pdf) == 0
+    ierr, ref, _ = O.gridsearch_f90(ld, n, nobs, 0, mask, c["tobs"], var, c["test"], np.float64)
+    assert np.array_equal(pdf, ref)
+    assert L.locate3d_gridsearch__double64(ld - 1, n, nobs, 1, mask, c["tobs"], var, c["test"], pdf) == 1
+    assert L.locate3d_gridsearch__double64(ld, n, nobs, 1, np.ones(nobs, np.int32), c["tobs"], var, c["test"], pdf) == 1
+    assert L.locate3d_gridsearch__double64(ld, n, nobs, 1, mask, c["tobs"], np.zeros(nobs), c["test"], pdf) == 1
+
+
+def _c1_case(nevents=100, n=50, nstat=20):
+    """BASELINE config 1: homogeneous analytic tables, 20 stations on the top face, 100 events."""
+    h, vp = 1000.0, 2000.0
+    rng = np.random.default_rng(2016)
+    sx = rng.integers(0, n, nstat) * h
+    sy = rng.integers(0, n, nstat) * h
+    sz = np.full(nstat, (n - 1) * h)
+    tables = cases.homog_tables(n, n, n, h, sx, sy, sz, vp)
+    cat = cases.synthetic_catalog(tables, nevents, seed=2017, mask_frac=0.0, variances=(0.25,))
+    return n, h, tables, cat
+
+
+@pytest.mark.parametrize("job", [2, 1])
+def test_c1_catalog_matches_oracle(gpu_ctx, job):
+    """locate3d_gridsearch drop-in on config 1: located nodes identical, hypo/t0 bit-equal to the oracle."""
+    from mceik_b200 import locate as L
+    n, h, tables, cat = _c1_case()
+    ngrd = n ** 3
+    X, Y, Z = cases.node_coords(n, n, n, h, h, h)
+    assert L.locate3d_initialize() == 0
+    L.locate3d_set_tables(tables, ngrd)
+    L.locate3d_set_grid(X, Y, Z)
+    hypo = np.zeros(4 * cat["nevents"])
+    ierr = L.locate3d_gridsearch(1, job, cat["nobs"], cat["nevents"], cat["luseObs"], cat["statPtr"], cat["pickType"],
+                                 cat["statCor"], cat["tori"], cat["varobs"], cat["tobs"], None, hypo)
+    assert ierr == 0
+    rc, hypo_ref, iopt_ref, obj_ref = O.locate3d_catalog(job, ngrd, ngrd, tables, cat["nobs"], cat["nevents"], cat["luseObs"],
+                                                         cat["statPtr"], cat["pickType"], cat["statCor"], cat["tori"],
+                                                         cat["varobs"], cat["tobs"], X, Y, Z)
+    assert rc == 0
+    assert np.array_equal(hypo, hypo_ref)
+    assert np.array_equal(iopt_ref, cat["true_node"])  # noise-free picks sit on a node
+    assert L.locate3d_gridsearch(1, 3, cat["nobs"], cat["nevents"], cat["luseObs"], cat["statPtr"], cat["pickType"],
+                                 cat["statCor"], cat["tori"], cat["varobs"], cat["tobs"], None, hypo) == 1
+    L.locate3d_finalize()
+
+
+def test_batched_ragged_catalog(gpu_ctx):
+    """Locator on a ragged CSR catalogue: masked picks, an event without picks, per-event table
+    order that differs between events, noisy picks (optimum off the true node)."""
+    from mceik_b200.locate import Locator
+    n, h, tables, _ = _c1_case(nevents=1, n=24, nstat=7)
+    ngrd = n ** 3
+    ntab = tables.shape[0]
+    rng = np.random.default_rng(99)
+    ne = 37
+    obs_ptr, tid, tc, var, tori = [0], [], [], [], rng.uniform(0, 5, ne)
+    for e in range(ne):
+        k = 0 if e == 5 else int(rng.integers(1, ntab + 1))
+        ids = rng.permutation(ntab)[:k]
+        node = int(rng.integers(0, ngrd))
+        for t in ids:
+            used = rng.random() > 0.15
+            tid.append(int(t) if used else -1)
+            tc.append(float(tables[t, node]) + tori[e] + rng.normal(0, 0.02))
+            var.append(float(rng.choice([0.1, 0.25, 0.5])))
+        obs_ptr.append(len(tid))
+    obs_ptr, tid, tc, var = np.array(obs_ptr, np.int32), np.array(tid, np.int32), np.array(tc), np.array(var)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    for job in (2, 1):
+        iopt, t0, obj = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
+        for e in range(ne):
+            b, en = obs_ptr[e], obs_ptr[e + 1]
+            k = en - b
+            use = (tid[b:en] >= 0).astype(np.int32)
+            if use.sum() == 0:
+                assert iopt[e] == -1
+                continue
+            stat = np.where(use == 1, tid[b:en] // 2 + 1, 1).astype(np.int32)
+            ph = np.where(use == 1, tid[b:en] % 2 + 1, 1).astype(np.int32)
+            rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, k, 1, use, stat, ph, np.zeros(k), tori[e:e + 1],
+                                                var[b:en], tc[b:en], np.zeros(ngrd), np.zeros(ngrd), np.zeros(ngrd))
+            assert rc == 0 and io[0] == iopt[e], f"event {e}"
+            assert ob[0] == obj[e] and hy[3] == t0[e]
+
+
+def test_catalog_struct_entry(gpu_ctx):
+    """mceik_locate_catalog with the mceik_struct.h layouts (CSR obsPtr, 1-based statPtr, P/S corrections)."""
+    from mceik_b200.locate import Locator
+    n, h, tables, cat = _c1_case(nevents=12, n=20, nstat=5)
+    ngrd = n ** 3
+    X, Y, Z = cases.node_coords(n, n, n, h, h, h)
+    nobs = cat["nobs"]
+    pcorr = np.linspace(-0.1, 0.1, 5)
+    scorr = np.linspace(0.2, -0.2, 5)
+    tobs = cat["tobs"].reshape(12, nobs).copy()
+    tobs[:, 0::2] += pcorr[None, :]
+    tobs[:, 1::2] += scorr[None, :]
+    catalog = dict(nevents=12, tori=cat["tori"], tobs=tobs.ravel(), varObs=cat["varobs"], luseObs=cat["luseObs"],
+                   pickType=cat["pickType"], statPtr=cat["statPtr"], obsPtr=np.arange(13, dtype=np.int32) * nobs)
+    stations = dict(nstat=5, pcorr=pcorr, scorr=scorr)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    loc.set_grid(X, Y, Z)
+    hypo, iopt, obj = loc.locate_catalog(catalog, stations, 2)
+    assert np.array_equal(iopt, cat["true_node"])
+    assert np.allclose(hypo[:, 3], cat["tori"], atol=1e-5)
+    assert np.array_equal(hypo[:, 0], X[iopt].astype(np.float64))
