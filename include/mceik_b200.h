@@ -168,6 +168,9 @@ int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
 int mceik_fsm_set_algo(mceik_ctx *ctx, int algo);
 /* Node-updates executed by the last solve on this context (N * 8 * iterations, summed over fields). */
 long long mceik_fsm_last_node_updates(mceik_ctx *ctx);
+/* Device time (ms, CUDA events on the context stream) and count of the sweep-kernel launches of the
+ * last solve: the numerator/denominator of the roofline figure bench.py reports. */
+int mceik_fsm_last_sweep_stats(mceik_ctx *ctx, double *sweep_ms, int *launches);
 
 /* Analytic homogeneous tables on the device: fp32 table t = dist/vel per station (homog.c:594-621
  * followed by homog.c:624-635).  d_tables [nstations][ldtab]; xs,ys,zs,vel are host arrays. */

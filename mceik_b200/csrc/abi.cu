@@ -44,6 +44,10 @@ struct mceik_ctx {
     bool own_stream = false;
     int fsm_algo = MCEIK_FSM_ALGO_TILES;
     long long last_updates = 0;
+    // device time of the sweep kernel launches of the last solve (CUDA events on ctx->stream)
+    double last_sweep_ms = 0.0;
+    int last_sweep_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     fsm::TilePlan plan;
     // eikonal workspaces
     DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
@@ -118,10 +122,16 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             return -1;
         }
     ctx->last_updates = 0;
+    ctx->last_sweep_ms = 0.0;
+    ctx->last_sweep_launches = 0;
     if (nfields == 0) return 0;
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->stream;
     const int nx = g->nx, ny = g->ny, nz = g->nz;
+    if (!ctx->ev0) {
+        MCEIK_CUDA(cudaEventCreate(&ctx->ev0));
+        MCEIK_CUDA(cudaEventCreate(&ctx->ev1));
+    }
 
     if (!d_u) d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * nfields));
     double *d_u0 = static_cast<double *>(ctx->ws_u0.ensure(sizeof(double) * N * nfields));
@@ -239,11 +249,19 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_tile = d_bctile; a.bc_local = d_bcloc;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)ngroups * pl.ntiles, st));
+            MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
             fsm::launch_iteration_tiles(a, st);
+            MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
+            ctx->last_sweep_launches += 1;
         }
         MCEIK_CUDA(cudaMemcpyAsync(h_nonconv.data(), d_nonconv, sizeof(unsigned long long) * nfields,
                                    cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaStreamSynchronize(st));
+        if (ctx->fsm_algo != MCEIK_FSM_ALGO_LEVELS) {
+            float ms = 0.f;
+            MCEIK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            ctx->last_sweep_ms += ms;
+        }
         std::vector<int> still;
         for (int f : active) {
             it[f] = k;
@@ -374,6 +392,8 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     } catch (...) {
     }
@@ -395,6 +415,12 @@ int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
     return 0;
 }
 long long mceik_fsm_last_node_updates(mceik_ctx *c) { return c ? c->last_updates : 0; }
+int mceik_fsm_last_sweep_stats(mceik_ctx *c, double *sweep_ms, int *launches) {
+    if (!c) return -1;
+    if (sweep_ms) *sweep_ms = c->last_sweep_ms;
+    if (launches) *launches = c->last_sweep_launches;
+    return 0;
+}
 
 int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow,
                                 int nfields, const int *field_model, const int *src_ptr, const double *ts,

@@ -104,6 +104,13 @@ class EikonalSolver:
         """N * 8 * iterations summed over the fields of the last solve."""
         return int(self.lib.mceik_fsm_last_node_updates(self.ctx.handle))
 
+    @property
+    def sweep_stats(self):
+        """(device ms spent in the sweep kernel, number of sweep-kernel launches) of the last solve."""
+        ms, n = C.c_double(0.0), C.c_int(0)
+        self.lib.mceik_fsm_last_sweep_stats(self.ctx.handle, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
     def solve_host(self, slow, field_model, ts, xs, ys, zs, src_ptr=None, want_u=True, want_tables=False, ldtab=None):
         """Host (numpy) buffers in and out.  slow: [nmodels, N] fp64.  Returns (u, tables, iters, ierr)."""
         slow = np.ascontiguousarray(slow, dtype=np.float64).reshape(-1, self.n)

@@ -29,7 +29,8 @@ ap.add_argument("--skip-gs", action="store_true")
 a = ap.parse_args()
 
 torch.cuda.set_device(0)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 ctx = mceik_b200.Context(0, stream=stream.cuda_stream)
 
 if not a.skip_fsm:
