@@ -139,7 +139,7 @@ typedef struct mceik_fsm_grid {
     int maxit;         /* iteration cap; one iteration = 8 sweeps */
 } mceik_fsm_grid;
 
-enum { MCEIK_FSM_ALGO_TILES = 0, MCEIK_FSM_ALGO_LEVELS = 1 };
+enum { MCEIK_FSM_ALGO_TILES = 0, MCEIK_FSM_ALGO_LEVELS = 1, MCEIK_FSM_ALGO_BRICKS = 2 };
 
 /*
  * Solve `nfields` independent eikonal fields in one call.

@@ -49,6 +49,8 @@ struct mceik_ctx {
     int last_sweep_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     fsm::TilePlan plan;
+    fsm::BrickPlan bplan;
+    int brick_zc = 64;
     // eikonal workspaces
     DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
     // locator state
@@ -137,6 +139,9 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     double *d_u0 = static_cast<double *>(ctx->ws_u0.ensure(sizeof(double) * N * nfields));
     ctx->plan.build(nx, ny, nz, st);
     const fsm::TilePlan &pl = ctx->plan;
+    const bool bricks = ctx->fsm_algo == MCEIK_FSM_ALGO_BRICKS;
+    if (bricks) ctx->bplan.build(nx, ny, nz, ctx->brick_zc, st);
+    const fsm::BrickPlan &bp = ctx->bplan;
 
     // ---- boundary conditions: stencil records per field (host), unique node lists per field
     std::vector<fsm::BcRecord> recs;
@@ -197,11 +202,13 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         if (!ferr[f]) active.push_back(f);
     // control block: [queue int (256 B)] [nonconv ull x nfields] [done int x ngroups*ntiles]
     const size_t c_nonconv = 256, c_done = align_up(c_nonconv + sizeof(unsigned long long) * nfields);
-    ctx->ws_ctrl.ensure(c_done + sizeof(int) * (size_t)nfields * pl.ntiles);
+    ctx->ws_ctrl.ensure(c_done + sizeof(int) * (size_t)nfields * std::max(pl.ntiles, bricks ? bp.nbricks : 0));
     char *ctrl = static_cast<char *>(ctx->ws_ctrl.p);
     unsigned long long *d_nonconv = reinterpret_cast<unsigned long long *>(ctrl + c_nonconv);
     std::vector<unsigned long long> h_nonconv(nfields);
 
+    if (bricks)  // u0 = u before the first iteration (fsm3d.f90:60); refreshed by the convergence kernel
+        MCEIK_CUDA(cudaMemcpyAsync(d_u0, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToDevice, st));
     uint8_t *d_lupd = nullptr;
     if (ctx->fsm_algo == MCEIK_FSM_ALGO_LEVELS) {
         d_lupd = static_cast<uint8_t *>(ctx->ws_lupd.ensure(N * nfields));
@@ -216,6 +223,25 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             const int *d_active = upload(ctx->ws_meta, o_active, active, st);
             fsm::launch_iteration_levels(nx, ny, nz, g->h, (int)active.size(), d_active, d_fmodel, d_slow, d_lupd,
                                          d_u, st);
+            fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
+        } else if (bricks) {
+            const int *d_active = upload(ctx->ws_meta, o_active, active, st);
+            fsm::BrickArgs a;
+            a.nx = nx; a.ny = ny; a.nz = nz;
+            a.nbx = bp.nbx; a.nby = bp.nby; a.nbz = bp.nbz; a.nbricks = bp.nbricks; a.nblevels = bp.nblevels; a.zc = bp.zc;
+            a.nfields_active = (int)active.size();
+            a.h = g->h;
+            a.active = d_active; a.field_model = d_fmodel; a.slow = d_slow; a.u = d_u;
+            a.brick_order = ctx->bplan.brick_order.as<int>();
+            a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
+            a.queue = reinterpret_cast<unsigned long long *>(ctrl);
+            a.done = reinterpret_cast<int *>(ctrl + c_done);
+            a.bc_ptr = d_bcptr; a.bc_node = d_recn;
+            MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
+            MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
+            fsm::launch_iteration_bricks(a, st);
+            MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
+            ctx->last_sweep_launches += 1;
             fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
         } else {
             // group the active fields by slowness model, up to kMaxSlots per CTA
@@ -389,6 +415,7 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         DeviceGuard dg(c->device);
         cudaStreamSynchronize(c->stream);
         c->plan.release();
+        c->bplan.release();
         for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
@@ -410,8 +437,9 @@ int mceik_ctx_synchronize(mceik_ctx *c) {
 }
 
 int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
-    if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS)) return -1;
+    if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS && algo != MCEIK_FSM_ALGO_BRICKS)) return -1;
     c->fsm_algo = algo;
+    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(64, atoi(e)));
     return 0;
 }
 long long mceik_fsm_last_node_updates(mceik_ctx *c) { return c ? c->last_updates : 0; }

@@ -19,45 +19,12 @@
 #include <algorithm>
 #include <vector>
 #include "fsm.cuh"
+#include "fsm_solve.cuh"
 
 namespace mceik {
 namespace fsm {
 
 __constant__ int c_lvl_ptr[kTileLevels + 1];
-
-// ------------------------------------------------------------------------------------------
-// Local Godunov solver: SORT3 + SOLVE_HAMILTONIAN2D/3D (fsm3d.f90:562-693), Zhao (2004)
-// eq. 2.4-2.6.  Explicit _rn intrinsics: the reference build has no fused multiply-add
-// (Makefile.inc:4-13), so none may appear here.  third / two_third are multiplied
-// (module.F90:7-8).  Returns DBL_MAX (u_nan) when no finite candidate exists.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double local_solve(double a, double b, double c, double f) {
-    const double kHuge = DBL_MAX;
-    const double lo = fmin(a, b), hi = fmax(a, b);
-    const double a1 = fmin(lo, c);
-    const double a3 = fmax(hi, c);
-    const double a2 = fmax(lo, fmin(hi, c));
-    if (a1 == kHuge) return kHuge;             // :664
-    double x = __dadd_rn(a1, f);               // p = 1 (:666)
-    if (x > a2) {
-        const double amb = __dsub_rn(a1, a2);  // SOLVE_HAMILTONIAN2D (:631-637)
-        if (fabs(amb) < f) {
-            const double arg = __dsub_rn(__dmul_rn(__dmul_rn(2.0, f), f), __dmul_rn(amb, amb));
-            x = __dmul_rn(0.5, __dadd_rn(__dadd_rn(a1, a2), __dsqrt_rn(arg)));
-        } else {
-            x = __dadd_rn(a1, f);              // MIN(a,b) + f with a1 <= a2
-        }
-        if (x > a3) {                          // p = 3 (:670-684)
-            const double qb = -__dmul_rn(2.0 / 3.0, __dadd_rn(__dadd_rn(a1, a2), a3));
-            const double sq = __dadd_rn(__dadd_rn(__dmul_rn(a1, a1), __dmul_rn(a2, a2)), __dmul_rn(a3, a3));
-            const double qc = __dmul_rn(__dsub_rn(sq, __dmul_rn(f, f)), 1.0 / 3.0);
-            const double disc = __dsub_rn(__dmul_rn(qb, qb), __dmul_rn(4.0, qc));
-            const double x3 = __dmul_rn(0.5, __dadd_rn(-qb, __dsqrt_rn(disc)));
-            x = (x3 < kHuge) ? x3 : kHuge;     // NaN (disc < 0) falls through to u_nan (:681-692)
-        }
-    }
-    return x;
-}
 
 // ------------------------------------------------------------------------------------------
 // fill + boundary conditions (EIKONAL3D_SETBCS, fsm3d.f90:782-834)

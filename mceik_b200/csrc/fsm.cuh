@@ -60,6 +60,36 @@ struct SweepArgs {
     const uint16_t *bc_local;   // i | j<<4 | k<<8 inside that tile
 };
 
+// Brick decomposition (8 x 8 x zc nodes) used by the streaming sweep kernel (fsm_bricks.cu).
+struct BrickPlan {
+    int nx = 0, ny = 0, nz = 0, zc = 0;
+    int nbx = 0, nby = 0, nbz = 0, nbricks = 0, nblevels = 0;
+    DevBuf brick_order;  // int[nbricks]: I | J<<10 | K<<20 sorted by I+J+K
+    DevBuf blevel_ptr;   // int[nblevels+1]
+    void build(int nx_, int ny_, int nz_, int zc_, cudaStream_t st);
+    void release();
+};
+
+// Arguments of one launch of the brick sweep kernel (= 8 sweeps of every active field).
+struct BrickArgs {
+    int nx, ny, nz;
+    int nbx, nby, nbz, nbricks, nblevels, zc;
+    int nfields_active;
+    double h;
+    const int *active;        // [nfields_active] field ids
+    const int *field_model;   // [nfields]
+    const double *slow;       // [nmodels][N]
+    double *u;                // [nfields][N]
+    const int *brick_order;
+    const int *blevel_ptr;
+    int *done;                    // [nfields][nbricks] sweeps completed per brick, zeroed per launch
+    unsigned long long *queue;    // [1] ticket counter, zeroed per launch
+    const int *bc_ptr;            // [nfields+1] CSR into bc_node
+    const int *bc_node;           // flat node index of each (unique) boundary-condition node
+};
+void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
+size_t bricks_smem_bytes();
+
 void launch_fill(double *d_u, size_t n, double value, cudaStream_t st);
 // One thread per field applies its BcRecords in source order.
 void launch_apply_bcs(int nfields, size_t n, const int *d_field_model, const int *d_rec_ptr,

@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import FsmGrid, c_dbl_p, c_flt_p, c_int_p
 
-ALGO_TILES, ALGO_LEVELS = 0, 1
+ALGO_TILES, ALGO_LEVELS, ALGO_BRICKS = 0, 1, 2
 
 
 def _i(v):

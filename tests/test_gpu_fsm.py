@@ -22,7 +22,7 @@ def _oracle_fields(nx, ny, nz, h, slow, fmodel, xs, ys, zs, ts, tol, maxit):
     return np.stack(out), np.array(its)
 
 
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_xfsm3d_case_matches_oracle(gpu_ctx, algo):
     """The reference's own driver case (fsm3d.f90:2085-2100): 70x80x90, h=100, v=5000, centre source."""
     from mceik_b200.eikonal import EikonalSolver
@@ -50,14 +50,15 @@ def test_random_model_two_sources_bit_exact(gpu_ctx, shape):
     zs = np.array([h * nz * 0.45, h * (nz - 2.5)])
     ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, ts, xs, ys, zs, tol=1e-6, maxit=20)
     assert ierr == 0
-    for algo in (0, 1):
+    for algo in (0, 1, 2):
         sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20, algo=algo)
         u, _, iters, ferr = sol.solve_host(slow[None], [0], ts, xs, ys, zs, src_ptr=[0, 2])
         assert ferr[0] == 0 and iters[0] == it
         assert np.array_equal(u[0], ref), f"algo {algo}: {np.count_nonzero(u[0] != ref)} nodes differ"
 
 
-def test_batched_fields_two_models(gpu_ctx):
+@pytest.mark.parametrize("algo", [0, 2])
+def test_batched_fields_two_models(gpu_ctx, algo):
     """7 fields over 2 slowness models (groups of 4, 1 and 2 slots), each equal to its own serial solve;
     fields converge after different iteration counts."""
     from mceik_b200.eikonal import EikonalSolver
@@ -68,7 +69,7 @@ def test_batched_fields_two_models(gpu_ctx):
     xs, ys, zs = cases.interior_sources(7, nx, ny, nz, h, seed=11)
     ts = np.linspace(0.0, 1.0, 7)
     ref, its = _oracle_fields(nx, ny, nz, h, slow, fmodel, xs, ys, zs, ts, 1e-6, 20)
-    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20, algo=algo)
     u, tab, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, want_tables=True)
     assert not ferr.any()
     assert np.array_equal(iters, its)
@@ -77,7 +78,8 @@ def test_batched_fields_two_models(gpu_ctx):
     assert sol.node_updates == int(n * 8 * its.sum())
 
 
-def test_c2_layered_128_bit_exact(gpu_ctx):
+@pytest.mark.parametrize("algo", [0, 2])
+def test_c2_layered_128_bit_exact(gpu_ctx, algo):
     """BASELINE config 2: 128^3, 1-D layered model, one station."""
     from mceik_b200.eikonal import EikonalSolver
     nx = ny = nz = 128
@@ -85,12 +87,13 @@ def test_c2_layered_128_bit_exact(gpu_ctx):
     slow = cases.layered_slowness(nx, ny, nz)
     xs, ys, zs = cases.interior_sources(1, nx, ny, nz, h, seed=1)
     ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs[0], ys[0], zs[0])
-    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, algo=algo)
     u, _, iters, ferr = sol.solve_host(slow[None], [0], [0.0], xs, ys, zs)
     assert iters[0] == it and np.array_equal(u[0], ref)
 
 
-def test_maxit_cap_and_edge_sources(gpu_ctx):
+@pytest.mark.parametrize("algo", [0, 2])
+def test_maxit_cap_and_edge_sources(gpu_ctx, algo):
     """maxit smaller than needed is not an error; a source on node 1 / outside the grid gives ierr=1
     for that field only (EIKONAL_INIT_GRID quirk, fsm3d.f90:736-751); a source on node nx-1 keeps two nodes."""
     from mceik_b200.eikonal import EikonalSolver
@@ -100,7 +103,7 @@ def test_maxit_cap_and_edge_sources(gpu_ctx):
     xs = np.array([h * 11.3, 0.0, h * (nx - 2), -5.0])
     ys = np.array([h * 7.7, h * 5.5, h * 9.0, h * 3.0])
     zs = np.array([h * 8.1, h * 5.5, h * 9.0, h * 3.0])
-    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-9, maxit=1)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-9, maxit=1, algo=algo)
     u, _, iters, ferr = sol.solve_host(slow[None], [0, 0, 0, 0], np.zeros(4), xs, ys, zs)
     assert list(ferr) == [0, 1, 0, 1]
     for f in (0, 2):

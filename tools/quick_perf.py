@@ -25,6 +25,7 @@ ap.add_argument("--gs-n", type=int, default=128)
 ap.add_argument("--gs-stations", type=int, default=32)
 ap.add_argument("--gs-events", type=int, default=512)
 ap.add_argument("--skip-fsm", action="store_true")
+ap.add_argument("--algo", type=int, default=0)
 ap.add_argument("--skip-gs", action="store_true")
 a = ap.parse_args()
 
@@ -39,7 +40,7 @@ if not a.skip_fsm:
     slow = torch.from_numpy(cases.checkerboard_slowness(n, n, n, cell=max(n // 8, 1))).cuda()
     xs, ys, zs = cases.interior_sources(a.fields, n, n, n, h, seed=3)
     d_u = torch.empty((a.fields, N), dtype=torch.float64, device="cuda")
-    sol = EikonalSolver(ctx, n, n, n, h)
+    sol = EikonalSolver(ctx, n, n, n, h, algo=a.algo)
     for rep in range(a.reps):
         torch.cuda.synchronize()
         t = time.time()
@@ -48,7 +49,7 @@ if not a.skip_fsm:
         dt = time.time() - t
         upd = sol.node_updates
         print(f"FSM {n}^3 x {a.fields} fields: iters={list(iters)} {dt*1e3:.1f} ms  {upd/dt/1e9:.2f} Gupd/s  "
-              f"{24*upd/dt/1e9:.0f} GB/s algorithmic", flush=True)
+              f"{24*upd/dt/1e9:.0f} GB/s algorithmic  sweep-kernel {sol.sweep_stats[0]:.1f} ms in {sol.sweep_stats[1]} launches", flush=True)
     del d_u
 
 if not a.skip_gs:
