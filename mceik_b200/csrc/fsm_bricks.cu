@@ -9,11 +9,11 @@
 //     section and marches along the brick axis: at step l it updates the nodes i + j + k = l, so a
 //     full hyperplane of the brick (64 nodes, 2 independent updates per lane) is in flight every
 //     step and there is no block-wide barrier anywhere -- only __syncwarp().
-//   * Planes of the brick stream through a per-warp shared-memory ring (19 planes of 10x10
-//     doubles: 8x8 nodes + halo) filled by cp.async two planes ahead with coalesced 64-byte rows,
-//     updated in place, and written back as soon as the last lane is done with a plane.  The
-//     slowness plane ring rides along.  Nothing but the ring is ever staged, so loads, the 2 x 64
-//     Godunov updates per step and stores overlap continuously.
+//   * The brick streams through a per-warp shared-memory ring of 11 skewed planes (10x10 travel-
+//     time cells + 8x8 slowness cells each) filled by cp.async two slots ahead in 32-byte sectors,
+//     updated in place, and written back as soon as a slot is final.  Nothing but the ring is ever
+//     staged, so loads, the 2 x 64 Godunov updates per step and stores overlap continuously, and
+//     15 warps (one brick each) are resident per SM.
 //   * Bricks form the same DAG as tiles; a persistent grid of independent warps pulls tickets in a
 //     topological order and spins on per-(field, brick) completion counters.
 #include <algorithm>
@@ -27,14 +27,22 @@ namespace fsm {
 namespace {
 
 constexpr int kBx = 8, kBy = 8;          // brick cross-section (nodes)
-constexpr int kPrefetch = 2;             // planes loaded ahead of the first reader
-constexpr int kRing = kPrefetch + 17;    // ring depth: (kBx-1)+(kBy-1) steps of life + store + prefetch
-constexpr int kURow = kBx + 2;           // ring row stride (doubles) with halo
-constexpr int kUPlane = kURow * (kBy + 2);
-constexpr int kFPlane = kBx * kBy;
+constexpr int kPrefetch = 2;             // ring slots loaded ahead of their first reader
+constexpr int kRing = 9 + kPrefetch;     // ring depth in slots (see "ring" below)
+constexpr int kURow = kBx + 2;           // cell row stride inside a slot (doubles), halo included
+constexpr int kUCells = kURow * (kBy + 2);
+constexpr int kSlot = kUCells + kBx * kBy;  // one slot: 10x10 travel-time cells + 8x8 slowness cells
 constexpr int kMaxZc = 64;               // longest brick (mask storage)
-constexpr int kWarpsPerCta = 8;
-constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * (kUPlane + kFPlane)) + sizeof(unsigned long long) * kMaxZc;
+constexpr int kWarpsPerCta = 15;
+// Progress word of a (field, brick): (sweeps completed << kProgShift) while idle, and
+// (sweep << kProgShift) + steps completed while the brick is being swept.
+constexpr int kProgShift = 12;
+constexpr int kPublish = 8;     // a sweeping warp publishes its progress every kPublish steps
+// A brick may run kLead steps behind its upwind x / y neighbours: the halo node it loads at step l
+// is in ring slot M = l + 4 + prefetch, and the neighbour wrote it back by its step M + 11 (y face;
+// M + 5 for the x face): the neighbour must have completed M + 12 steps.
+constexpr int kLead = 11;
+constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc;
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -44,14 +52,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// x-group of a cell column: i = -1 -> 0, 0..3 -> 1, 4..7 -> 2, 8 -> 3 (one 32-byte sector each)
+__device__ __forceinline__ int xgroup(int i) { return (i + 4) >> 2; }
+
 }  // namespace
 
+// The ring.  Cell (i, j, k) of the brick (halo: i, j in [-1, 8], k in [-1, ez]) lives in ring slot
+//     m = xgroup(i) + (j + 1) + (k + 1)        (mod kRing)
+// at cell offset (j+1)*10 + (i+1): a slot is a *skewed* plane made of sixteen 4-node x-sectors, one
+// per (x-group, j), so that global traffic stays sector-granular (32 B) while a slot only lives
+// from the step its first node is read to the step its last node is final: the node (i, j, k)
+// is updated at step l = i + j + k, i.e. in slot l + c with c = xgroup(i) - i + 2 in [-3, 3], and
+// reads slots m-1, m, m+1 only.  Slot m is first read at step m-4, last written at step m+3 and
+// last read at step m+4, so kRing = 9 + prefetch slots suffice (19 planes would be needed without
+// the skew), which is what lets 15 independent warps share one SM's shared memory.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(const BrickArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kBy+2][kBx+2]
-    double *F = U + kRing * kUPlane;                                              // [kRing][kBy][kBx]
-    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(F + kRing * kFPlane);  // [kMaxZc]
+    double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
+    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc]
 
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const size_t nxy = (size_t)nx * ny, N = nxy * nz;
@@ -59,6 +78,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
     const long long per_sweep = (long long)a.nbricks * nf;
     const long long ntasks = 8 * per_sweep;
     const int li = lane & 7, jq = lane >> 3;  // lane -> columns (li, jq) and (li, jq + 4)
+    const int ig = xgroup(li);
+    // this lane's halo cell: lanes 0-7: (i=-1, j=lane); 8-15: (i=8, j); 16-23: (i, j=-1); 24-31: (i, j=8)
+    int hi_i, hi_j;
+    if (lane < 8) { hi_i = -1; hi_j = lane; }
+    else if (lane < 16) { hi_i = kBx; hi_j = lane - 8; }
+    else if (lane < 24) { hi_i = lane - 16; hi_j = -1; }
+    else { hi_i = lane - 24; hi_j = kBy; }
+    const int cu0 = (jq + 1) * kURow + (li + 1), cu1 = (jq + 5) * kURow + (li + 1);  // cell offsets in a slot
+    const int cuh = (hi_j + 1) * kURow + (hi_i + 1);
+    const int cf0 = kUCells + jq * kBx + li, cf1 = kUCells + (jq + 4) * kBx + li;
+    const int kofs0 = ig + jq + 2, kofs1 = kofs0 + 4, kofsh = xgroup(hi_i) + hi_j + 2;  // k = m - kofs
+    const bool xm_prev = (li & 3) == 0, xp_next = (li & 3) == 3;  // x-neighbour in the previous / next slot
 
     while (true) {
         long long t = 0;
@@ -86,7 +117,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
         const int brick = (K * a.nby + J) * a.nbx + I;
         int *done_f = a.done + (size_t)f * a.nbricks;
 
-        // ---- dependencies: this brick and its 6 neighbours finished sweep s-1, upwind ones sweep s
+        // ---- dependencies (coarse): this brick and its 6 neighbours finished sweep s-1; the upwind z
+        //      neighbour finished sweep s.  The upwind x / y neighbours only need a kLead-step head
+        //      start, which is checked every kPublish steps inside the sweep loop (fine-grained
+        //      pipelining of the brick wavefront).
+        const int *up_ptr = nullptr;  // lanes 0 / 1: progress word of the upwind x / y neighbour
         if (lane < 7) {
             int di = 0, dj = 0, dk = 0;
             if (lane == 1) di = -1; else if (lane == 2) di = 1;
@@ -94,14 +129,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             else if (lane == 5) dk = -1; else if (lane == 6) dk = 1;
             const int NI = I + di, NJ = J + dj, NK = K + dk;
             if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby && NK >= 0 && NK < a.nbz) {
-                int need = s;
-                if ((di != 0 && di == (revx ? 1 : -1)) || (dj != 0 && dj == (revy ? 1 : -1)) ||
-                    (dk != 0 && dk == (revz ? 1 : -1)))
-                    need = s + 1;
+                int need = s << kProgShift;
+                if (dk != 0 && dk == (revz ? 1 : -1)) need = (s + 1) << kProgShift;
                 const int *p = done_f + ((NK * a.nby + NJ) * a.nbx + NI);
-                while (ld_acquire_gpu(p) < need) __nanosleep(64);
+                while (ld_acquire_gpu(p) < need) __nanosleep(200);
             }
         }
+        if (lane < 2) {
+            const int NI = I + (lane == 0 ? (revx ? 1 : -1) : 0), NJ = J + (lane == 1 ? (revy ? 1 : -1) : 0);
+            if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby) up_ptr = done_f + ((K * a.nby + NJ) * a.nbx + NI);
+        }
+        auto wait_upwind = [&](int steps_needed) {  // upwind x / y neighbours have completed that many steps
+            if (up_ptr) {
+                const int need = (s << kProgShift) + steps_needed;
+                while (ld_acquire_gpu(up_ptr) < need) __nanosleep(100);
+            }
+            __syncwarp();
+        };
+        wait_upwind(4 + kPrefetch + kLead);  // the prologue issues slots 0 .. 3 + kPrefetch
         __syncwarp();
 
         // brick extent in memory coordinates and the sweep-oriented local frame:
@@ -142,90 +187,98 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             }
         }
 
-        // per-lane global offsets of its two interior columns and of its one halo cell, at plane k = 0
+        // per-lane global offsets (elements) of its two interior columns and of its halo column
         const int gxi = min(max(xb + sx * li, 0), nx - 1);
-        const int gy0 = min(max(yb + sy * jq, 0), ny - 1), gy1 = min(max(yb + sy * (jq + 4), 0), ny - 1);
-        const size_t col0 = (size_t)gy0 * nx + gxi, col1 = (size_t)gy1 * nx + gxi;
-        // halo cell of this lane: lanes 0-7: (i=-1, j=lane); 8-15: (i=8, j); 16-23: (i, j=-1); 24-31: (i, j=8)
-        int hi_i, hi_j;
-        if (lane < 8) { hi_i = -1; hi_j = lane; }
-        else if (lane < 16) { hi_i = kBx; hi_j = lane - 8; }
-        else if (lane < 24) { hi_i = lane - 16; hi_j = -1; }
-        else { hi_i = lane - 24; hi_j = kBy; }
+        const size_t col0 = (size_t)min(max(yb + sy * jq, 0), ny - 1) * nx + gxi;
+        const size_t col1 = (size_t)min(max(yb + sy * (jq + 4), 0), ny - 1) * nx + gxi;
         const size_t colh = (size_t)min(max(yb + sy * hi_j, 0), ny - 1) * nx + min(max(xb + sx * hi_i, 0), nx - 1);
-        const int soff0 = (jq + 1) * kURow + (li + 1), soff1 = (jq + 5) * kURow + (li + 1);
-        const int soffh = (hi_j + 1) * kURow + (hi_i + 1);
-        const int foff0 = jq * kBx + li, foff1 = (jq + 4) * kBx + li;
+        auto zoff = [&](int k) { return (size_t)min(max(zb + sz * k, 0), nz - 1) * nxy; };
 
-        // plane kk in [-1, ez] lives in ring slot (kk + 1) % kRing
-        auto issue_plane = [&](int kk) {
-            if (kk <= ez) {
-                const int slot = (kk + 1) % kRing;
-                const size_t zoff = (size_t)min(max(zb + sz * kk, 0), nz - 1) * nxy;
-                double *up = U + slot * kUPlane;
-                cp_async8(up + soff0, uf + zoff + col0);
-                cp_async8(up + soff1, uf + zoff + col1);
-                if (kk >= 0 && kk < ez) {
-                    cp_async8(up + soffh, uf + zoff + colh);
-                    double *fp = F + slot * kFPlane;
-                    cp_async8(fp + foff0, sl + zoff + col0);
-                    cp_async8(fp + foff1, sl + zoff + col1);
-                }
+        int ld_slot = 0;  // element offset of the ring slot the next issue_slot() fills
+        int ld_m = 0;
+        auto issue_slot = [&]() {
+            double *sp = U + ld_slot;
+            const int k0 = ld_m - kofs0, k1 = ld_m - kofs1, kh = ld_m - kofsh;
+            if (k0 >= -1 && k0 <= ez) {
+                const size_t z = zoff(k0);
+                cp_async8(sp + cu0, uf + z + col0);
+                if (k0 >= 0 && k0 < ez) cp_async8(sp + cf0, sl + z + col0);
             }
+            if (k1 >= -1 && k1 <= ez) {
+                const size_t z = zoff(k1);
+                cp_async8(sp + cu1, uf + z + col1);
+                if (k1 >= 0 && k1 < ez) cp_async8(sp + cf1, sl + z + col1);
+            }
+            if (kh >= 0 && kh < ez) cp_async8(sp + cuh, uf + zoff(kh) + colh);
             cp_async_commit();
+            ++ld_m;
+            ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
         };
-
-        for (int kk = -1; kk <= kPrefetch; ++kk) issue_plane(kk);
+        for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot();
 
         const bool act0 = li < ex && jq < ey, act1 = li < ex && jq + 4 < ey;
-        const int span = (ex - 1) + (ey - 1);
-        const int nsteps = ez + span;
+        // slot offsets of the node this lane updates at step l: m = l + c, c = ig - li + 2
+        int mc = ig - li + 2;                       // slot number at l = 0 (may be negative)
+        int oc = ((mc % kRing) + kRing) % kRing * kSlot;
+        int om = (oc == 0) ? (kRing - 1) * kSlot : oc - kSlot;
+        int op = (oc + kSlot == kRing * kSlot) ? 0 : oc + kSlot;
+        int st_slot = ((-3 % kRing) + kRing) % kRing * kSlot;  // slot l - 3 at l = 0
+        const int nsteps = ez + 14;
         for (int l = 0; l < nsteps; ++l) {
-            issue_plane(l + 1 + kPrefetch);
-            cp_async_wait<kPrefetch>();  // planes <= l + 1 have landed (for this lane)
+            if ((l & (kPublish - 1)) == 0) wait_upwind(l + kPublish + 4 + kPrefetch + kLead);
+            issue_slot();
+            cp_async_wait<kPrefetch>();  // slots <= l + 4 have landed (for this lane)
             __syncwarp();                // ... and for every lane of the warp
 
             const int k0 = l - li - jq, k1 = k0 - 4;
-            const bool do0 = act0 && k0 >= 0 && k0 < ez && !(hasbc && ((bcm[max(k0, 0)] >> (jq * kBx + li)) & 1ULL));
-            const bool do1 = act1 && k1 >= 0 && k1 < ez && !(hasbc && ((bcm[max(k1, 0)] >> ((jq + 4) * kBx + li)) & 1ULL));
+            bool do0 = act0 && k0 >= 0 && k0 < ez, do1 = act1 && k1 >= 0 && k1 < ez;
+            if (hasbc) {
+                if (do0 && ((bcm[k0] >> (jq * kBx + li)) & 1ULL)) do0 = false;
+                if (do1 && ((bcm[k1] >> ((jq + 4) * kBx + li)) & 1ULL)) do1 = false;
+            }
+            const double *pm = U + om, *pc = U + oc, *pp = U + op;
+            const double *pxm = xm_prev ? pm : pc, *pxp = xp_next ? pp : pc;
             double n0 = 0.0, n1 = 0.0, c0 = 0.0, c1 = 0.0;
-            double *p0 = nullptr, *p1 = nullptr;
             if (do0) {
-                const int sm = k0 % kRing, sc = (k0 + 1) % kRing, sp = (k0 + 2) % kRing;
-                p0 = U + sc * kUPlane + soff0;
-                c0 = *p0;
-                const double ux = fmin(p0[-1], p0[1]);
-                const double uy = fmin(p0[-kURow], p0[kURow]);
-                const double uz = fmin(U[sm * kUPlane + soff0], U[sp * kUPlane + soff0]);
-                n0 = local_solve_sl(ux, uy, uz, __dmul_rn(F[sc * kFPlane + foff0], a.h));
+                c0 = pc[cu0];
+                const double ux = dmin2(pxm[cu0 - 1], pxp[cu0 + 1]);
+                const double uy = dmin2(pm[cu0 - kURow], pp[cu0 + kURow]);
+                const double uz = dmin2(pm[cu0], pp[cu0]);
+                n0 = local_solve_sl(ux, uy, uz, __dmul_rn(pc[cf0], a.h));
             }
             if (do1) {
-                const int sm = k1 % kRing, sc = (k1 + 1) % kRing, sp = (k1 + 2) % kRing;
-                p1 = U + sc * kUPlane + soff1;
-                c1 = *p1;
-                const double ux = fmin(p1[-1], p1[1]);
-                const double uy = fmin(p1[-kURow], p1[kURow]);
-                const double uz = fmin(U[sm * kUPlane + soff1], U[sp * kUPlane + soff1]);
-                n1 = local_solve_sl(ux, uy, uz, __dmul_rn(F[sc * kFPlane + foff1], a.h));
+                c1 = pc[cu1];
+                const double ux = dmin2(pxm[cu1 - 1], pxp[cu1 + 1]);
+                const double uy = dmin2(pm[cu1 - kURow], pp[cu1 + kURow]);
+                const double uz = dmin2(pm[cu1], pp[cu1]);
+                n1 = local_solve_sl(ux, uy, uz, __dmul_rn(pc[cf1], a.h));
             }
-            if (do0 && n0 < c0) *p0 = n0;  // u = MIN(u, ubar) (fsm3d.f90:477)
-            if (do1 && n1 < c1) *p1 = n1;
+            if (do0 && n0 < c0) U[oc + cu0] = n0;  // u = MIN(u, ubar) (fsm3d.f90:477)
+            if (do1 && n1 < c1) U[oc + cu1] = n1;
             __syncwarp();
 
-            // plane kd is final once the last lane (i = ex-1, j = ey-1) has passed it: write it back
-            const int kd = l - span;
-            if (kd >= 0) {
-                const int slot = (kd + 1) % kRing;
-                const size_t zoff = (size_t)(zb + sz * kd) * nxy;
-                if (act0) __stcg(uf + zoff + col0, U[slot * kUPlane + soff0]);
-                if (act1) __stcg(uf + zoff + col1, U[slot * kUPlane + soff1]);
+            // slot l - 3 is final now: write its nodes back (32-byte sectors, one per lane quad)
+            {
+                const int ks0 = l - 3 - kofs0, ks1 = ks0 - 4;
+                if (act0 && ks0 >= 0 && ks0 < ez) __stcg(uf + zoff(ks0) + col0, U[st_slot + cu0]);
+                if (act1 && ks1 >= 0 && ks1 < ez) __stcg(uf + zoff(ks1) + col1, U[st_slot + cu1]);
+            }
+            om = oc; oc = op;
+            op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
+            st_slot = (st_slot + kSlot == kRing * kSlot) ? 0 : st_slot + kSlot;
+            if (((l + 1) & (kPublish - 1)) == 0 && l + 1 < nsteps) {  // publish progress
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(done_f + brick, (s << kProgShift) + l + 1);
+                }
             }
         }
         cp_async_wait<0>();
         __syncwarp();
         if (lane == 0) {
             __threadfence();
-            red_release_gpu_add(done_f + brick, 1);
+            st_release_gpu(done_f + brick, (s + 1) << kProgShift);
         }
         __syncwarp();
     }
