@@ -164,13 +164,20 @@ int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
                                 int nfields, const int *field_model, const int *src_ptr,
                                 const double *ts, const double *xs, const double *ys, const double *zs,
                                 double *d_u, float *d_tables, size_t ldtab, int *iters, int *field_ierr);
-/* Select the sweep kernel (default MCEIK_FSM_ALGO_TILES). */
+/* Select the sweep kernel: BRICKS (default; warp-per-brick streaming kernel, fsm_bricks.cu), TILES
+ * (CTA-per-16^3-tile kernel, fsm.cu) or LEVELS (one launch per hyperplane; cross-check path). */
 int mceik_fsm_set_algo(mceik_ctx *ctx, int algo);
 /* Node-updates executed by the last solve on this context (N * 8 * iterations, summed over fields). */
 long long mceik_fsm_last_node_updates(mceik_ctx *ctx);
 /* Device time (ms, CUDA events on the context stream) and count of the sweep-kernel launches of the
  * last solve: the numerator/denominator of the roofline figure bench.py reports. */
 int mceik_fsm_last_sweep_stats(mceik_ctx *ctx, double *sweep_ms, int *launches);
+
+/* Device self-test of the sweep kernels' arithmetic building blocks: the branch-free square root
+ * and the straight-line local solver must equal __dsqrt_rn and the reference-ordered solver bit
+ * for bit on `samples` pseudo-random inputs.  Outputs the number of mismatches (expected 0). */
+int mceik_selftest_solver(mceik_ctx *ctx, unsigned long long seed, long long samples, long long *bad_sqrt,
+                          long long *bad_solve);
 
 /* Analytic homogeneous tables on the device: fp32 table t = dist/vel per station (homog.c:594-621
  * followed by homog.c:624-635).  d_tables [nstations][ldtab]; xs,ys,zs,vel are host arrays. */

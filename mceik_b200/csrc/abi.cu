@@ -42,7 +42,7 @@ struct mceik_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    int fsm_algo = MCEIK_FSM_ALGO_TILES;
+    int fsm_algo = MCEIK_FSM_ALGO_BRICKS;
     long long last_updates = 0;
     // device time of the sweep kernel launches of the last solve (CUDA events on ctx->stream)
     double last_sweep_ms = 0.0;
@@ -237,6 +237,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
+            a.stats = getenv("MCEIK_FSM_STATS") ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
             MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
             fsm::launch_iteration_bricks(a, st);
@@ -283,6 +284,12 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         MCEIK_CUDA(cudaMemcpyAsync(h_nonconv.data(), d_nonconv, sizeof(unsigned long long) * nfields,
                                    cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaStreamSynchronize(st));
+        if (bricks && getenv("MCEIK_FSM_STATS")) {
+            unsigned long long hs[4];
+            MCEIK_CUDA(cudaMemcpy(hs, ctrl + 64, sizeof(hs), cudaMemcpyDeviceToHost));
+            if (hs[3]) printf("[fsm stats] iter %d: tasks %llu  avg cycles: start-wait %.0f  upwind-wait %.0f  run %.0f\n", k, hs[3],
+                              (double)hs[0] / hs[3], (double)hs[1] / hs[3], (double)hs[2] / hs[3]);
+        }
         if (ctx->fsm_algo != MCEIK_FSM_ALGO_LEVELS) {
             float ms = 0.f;
             MCEIK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -448,6 +455,24 @@ int mceik_fsm_last_sweep_stats(mceik_ctx *c, double *sweep_ms, int *launches) {
     if (sweep_ms) *sweep_ms = c->last_sweep_ms;
     if (launches) *launches = c->last_sweep_launches;
     return 0;
+}
+
+int mceik_selftest_solver(mceik_ctx *ctx, unsigned long long seed, long long samples, long long *bad_sqrt,
+                          long long *bad_solve) {
+    return guarded([&]() -> int {
+        if (!ctx || !bad_sqrt || !bad_solve) return -1;
+        DeviceGuard dg(ctx->device);
+        unsigned long long *d = static_cast<unsigned long long *>(ctx->ws_ctrl.ensure(256));
+        MCEIK_CUDA(cudaMemsetAsync(d, 0, 16, ctx->stream));
+        const int blocks = 148 * 8, per = (int)std::max<long long>(1, samples / (blocks * 256LL));
+        fsm::launch_selftest(seed, blocks, per, d, ctx->stream);
+        unsigned long long h[2] = {0, 0};
+        MCEIK_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
+        *bad_sqrt = (long long)h[0];
+        *bad_solve = (long long)h[1];
+        return 0;
+    });
 }
 
 int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow,

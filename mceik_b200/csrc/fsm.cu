@@ -249,6 +249,52 @@ __global__ void __launch_bounds__(B *kGroupThreads, 1) sweep_tiles_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// self-test: sqrt_fast(x) == __dsqrt_rn(x) bit for bit, and local_solve_sl == local_solve
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long &z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    unsigned long long x = z;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+
+__global__ void selftest_kernel(unsigned long long seed, int per_thread, unsigned long long *bad) {
+    unsigned long long z = seed + 0x632be59bd9b4e019ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x);
+    unsigned long long nbad_sqrt = 0, nbad_solve = 0;
+    for (int it = 0; it < per_thread; ++it) {
+        // sqrt: random mantissa, exponent uniform over the admitted range, plus near-square inputs
+        const unsigned long long r = splitmix(z);
+        const int ex = 64 + (int)(splitmix(z) % 1982);  // biased exponent in [64, 2045]
+        double x = __longlong_as_double((r & 0x000fffffffffffffULL) | ((unsigned long long)ex << 52));
+        if ((it & 3) == 3) { const double q = 1.0 + (double)(r >> 12) * 0x1p-52; x = q * q; }
+        if (x >= MCEIK_SQRT_FAST_MIN && x < DBL_MAX) {
+            if (__double_as_longlong(sqrt_fast(x)) != __double_as_longlong(__dsqrt_rn(x))) ++nbad_sqrt;
+        }
+        // solver: three neighbour times around a base value, f comparable to their spread
+        const double base = (double)(splitmix(z) >> 40) * 1e-4;
+        const double f = 1e-3 + (double)(splitmix(z) >> 44) * 1e-6;
+        double n[3];
+        for (int q = 0; q < 3; ++q) {
+            const unsigned long long w = splitmix(z);
+            n[q] = ((w & 15) == 0) ? DBL_MAX : base + f * 4.0 * ((double)(w >> 11) * 0x1p-53);
+            if ((w & 0xf0) == 0x10) n[q] = n[(q + 2) % 3 < q ? (q + 2) % 3 : 0];  // exact ties
+        }
+        bool rare;
+        double a = local_solve_sl(n[0], n[1], n[2], f, rare);
+        if (rare) a = local_solve(n[0], n[1], n[2], f);
+        if (__double_as_longlong(a) != __double_as_longlong(local_solve(n[0], n[1], n[2], f))) ++nbad_solve;
+    }
+    if (nbad_sqrt) atomicAdd(bad, nbad_sqrt);
+    if (nbad_solve) atomicAdd(bad + 1, nbad_solve);
+}
+
+void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st) {
+    selftest_kernel<<<blocks, 256, 0, st>>>(seed, per_thread, d_bad);
+    MCEIK_LAUNCH_CHECK();
+}
+
 size_t tiles_smem_bytes(int nslots) {
     return (size_t)nslots * kHaloNodes * sizeof(double) + kTileNodes * sizeof(double) +
            kTileNodes * sizeof(uint16_t) + (size_t)nslots * (kTileNodes / 32) * sizeof(uint32_t);

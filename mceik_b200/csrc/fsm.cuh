@@ -86,10 +86,13 @@ struct BrickArgs {
     unsigned long long *queue;    // [1] ticket counter, zeroed per launch
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
     const int *bc_node;           // flat node index of each (unique) boundary-condition node
+    unsigned long long *stats;    // optional [4] cycle counters (MCEIK_FSM_STATS=1), else nullptr
 };
 void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
 size_t bricks_smem_bytes();
 
+// device self-test of sqrt_fast / local_solve_sl against __dsqrt_rn / local_solve; d_bad[2] counts mismatches
+void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st);
 void launch_fill(double *d_u, size_t n, double value, cudaStream_t st);
 // One thread per field applies its BcRecords in source order.
 void launch_apply_bcs(int nfields, size_t n, const int *d_field_model, const int *d_rec_ptr,

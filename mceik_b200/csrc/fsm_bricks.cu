@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
     const int cu0 = (jq + 1) * kURow + (li + 1), cu1 = (jq + 5) * kURow + (li + 1);  // cell offsets in a slot
     const int cuh = (hi_j + 1) * kURow + (hi_i + 1);
     const int cf0 = kUCells + jq * kBx + li, cf1 = kUCells + (jq + 4) * kBx + li;
-    const int kofs0 = ig + jq + 2, kofs1 = kofs0 + 4, kofsh = xgroup(hi_i) + hi_j + 2;  // k = m - kofs
+    const int kofs0 = ig + jq + 2, kofsh = xgroup(hi_i) + hi_j + 2;  // k = m - kofs (second column: kofs0 + 4)
     const bool xm_prev = (li & 3) == 0, xp_next = (li & 3) == 3;  // x-neighbour in the previous / next slot
 
     while (true) {
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
         const int brick = (K * a.nby + J) * a.nbx + I;
         int *done_f = a.done + (size_t)f * a.nbricks;
 
+        const long long t_start = a.stats ? clock64() : 0;
         // ---- dependencies (coarse): this brick and its 6 neighbours finished sweep s-1; the upwind z
         //      neighbour finished sweep s.  The upwind x / y neighbours only need a kLead-step head
         //      start, which is checked every kPublish steps inside the sweep loop (fine-grained
@@ -132,20 +133,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
                 int need = s << kProgShift;
                 if (dk != 0 && dk == (revz ? 1 : -1)) need = (s + 1) << kProgShift;
                 const int *p = done_f + ((NK * a.nby + NJ) * a.nbx + NI);
-                while (ld_acquire_gpu(p) < need) __nanosleep(200);
+                while (ld_acquire_gpu(p) < need) __nanosleep(400);
             }
         }
         if (lane < 2) {
             const int NI = I + (lane == 0 ? (revx ? 1 : -1) : 0), NJ = J + (lane == 1 ? (revy ? 1 : -1) : 0);
             if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby) up_ptr = done_f + ((K * a.nby + NJ) * a.nbx + NI);
         }
+        long long t_upwind = 0;
         auto wait_upwind = [&](int steps_needed) {  // upwind x / y neighbours have completed that many steps
+            const long long t0 = a.stats ? clock64() : 0;
             if (up_ptr) {
                 const int need = (s << kProgShift) + steps_needed;
-                while (ld_acquire_gpu(up_ptr) < need) __nanosleep(100);
+                while (ld_acquire_gpu(up_ptr) < need) __nanosleep(200);
             }
             __syncwarp();
+            if (a.stats) t_upwind += clock64() - t0;
         };
+        const long long t_deps = a.stats ? clock64() : 0;
         wait_upwind(4 + kPrefetch + kLead);  // the prologue issues slots 0 .. 3 + kPrefetch
         __syncwarp();
 
@@ -187,29 +192,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             }
         }
 
-        // per-lane global offsets (elements) of its two interior columns and of its halo column
+        // per-lane base pointers (plane k = 0) of its two interior columns and of its halo column;
+        // plane k sits at base + kclamp(k) * zstride, where kclamp folds the two z-halo planes
+        // (k = -1, k = ez) back onto the boundary plane when the brick touches the grid boundary.
         const int gxi = min(max(xb + sx * li, 0), nx - 1);
-        const size_t col0 = (size_t)min(max(yb + sy * jq, 0), ny - 1) * nx + gxi;
-        const size_t col1 = (size_t)min(max(yb + sy * (jq + 4), 0), ny - 1) * nx + gxi;
-        const size_t colh = (size_t)min(max(yb + sy * hi_j, 0), ny - 1) * nx + min(max(xb + sx * hi_i, 0), nx - 1);
-        auto zoff = [&](int k) { return (size_t)min(max(zb + sz * k, 0), nz - 1) * nxy; };
+        const size_t col0 = (size_t)zb * nxy + (size_t)min(max(yb + sy * jq, 0), ny - 1) * nx + gxi;
+        const size_t col1 = (size_t)zb * nxy + (size_t)min(max(yb + sy * (jq + 4), 0), ny - 1) * nx + gxi;
+        const size_t colh = (size_t)zb * nxy + (size_t)min(max(yb + sy * hi_j, 0), ny - 1) * nx + min(max(xb + sx * hi_i, 0), nx - 1);
+        double *pu0 = uf + col0, *pu1 = uf + col1;
+        const double *puh = uf + colh, *pf0 = sl + col0, *pf1 = sl + col1;
+        const long long zstride = (long long)sz * (long long)nxy;
+        const int klo = (zb - sz < 0 || zb - sz > nz - 1) ? 0 : -1;             // plane index used for k = -1
+        const int khi = (zb + sz * ez < 0 || zb + sz * ez > nz - 1) ? ez - 1 : ez;  // ... and for k = ez
 
         int ld_slot = 0;  // element offset of the ring slot the next issue_slot() fills
         int ld_m = 0;
         auto issue_slot = [&]() {
             double *sp = U + ld_slot;
-            const int k0 = ld_m - kofs0, k1 = ld_m - kofs1, kh = ld_m - kofsh;
+            const int k0 = ld_m - kofs0, k1 = k0 - 4, kh = ld_m - kofsh;
             if (k0 >= -1 && k0 <= ez) {
-                const size_t z = zoff(k0);
-                cp_async8(sp + cu0, uf + z + col0);
-                if (k0 >= 0 && k0 < ez) cp_async8(sp + cf0, sl + z + col0);
+                const long long z = (long long)min(max(k0, klo), khi) * zstride;
+                cp_async8(sp + cu0, pu0 + z);
+                if (k0 >= 0 && k0 < ez) cp_async8(sp + cf0, pf0 + z);
             }
             if (k1 >= -1 && k1 <= ez) {
-                const size_t z = zoff(k1);
-                cp_async8(sp + cu1, uf + z + col1);
-                if (k1 >= 0 && k1 < ez) cp_async8(sp + cf1, sl + z + col1);
+                const long long z = (long long)min(max(k1, klo), khi) * zstride;
+                cp_async8(sp + cu1, pu1 + z);
+                if (k1 >= 0 && k1 < ez) cp_async8(sp + cf1, pf1 + z);
             }
-            if (kh >= 0 && kh < ez) cp_async8(sp + cuh, uf + zoff(kh) + colh);
+            if (kh >= 0 && kh < ez) cp_async8(sp + cuh, puh + (long long)kh * zstride);
             cp_async_commit();
             ++ld_m;
             ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
@@ -236,23 +247,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
                 if (do0 && ((bcm[k0] >> (jq * kBx + li)) & 1ULL)) do0 = false;
                 if (do1 && ((bcm[k1] >> ((jq + 4) * kBx + li)) & 1ULL)) do1 = false;
             }
+            // Both nodes of the lane are evaluated unconditionally and side by side (two independent
+            // dependency chains for the scheduler to interleave); only the final store is predicated.
+            // An inactive node reads valid ring cells whose values are simply not used.
             const double *pm = U + om, *pc = U + oc, *pp = U + op;
             const double *pxm = xm_prev ? pm : pc, *pxp = xp_next ? pp : pc;
-            double n0 = 0.0, n1 = 0.0, c0 = 0.0, c1 = 0.0;
-            if (do0) {
-                c0 = pc[cu0];
-                const double ux = dmin2(pxm[cu0 - 1], pxp[cu0 + 1]);
-                const double uy = dmin2(pm[cu0 - kURow], pp[cu0 + kURow]);
-                const double uz = dmin2(pm[cu0], pp[cu0]);
-                n0 = local_solve_sl(ux, uy, uz, __dmul_rn(pc[cf0], a.h));
-            }
-            if (do1) {
-                c1 = pc[cu1];
-                const double ux = dmin2(pxm[cu1 - 1], pxp[cu1 + 1]);
-                const double uy = dmin2(pm[cu1 - kURow], pp[cu1 + kURow]);
-                const double uz = dmin2(pm[cu1], pp[cu1]);
-                n1 = local_solve_sl(ux, uy, uz, __dmul_rn(pc[cf1], a.h));
-            }
+            const double c0 = pc[cu0], c1 = pc[cu1];
+            const double ux0 = dmin2(pxm[cu0 - 1], pxp[cu0 + 1]), ux1 = dmin2(pxm[cu1 - 1], pxp[cu1 + 1]);
+            const double uy0 = dmin2(pm[cu0 - kURow], pp[cu0 + kURow]), uy1 = dmin2(pm[cu1 - kURow], pp[cu1 + kURow]);
+            const double uz0 = dmin2(pm[cu0], pp[cu0]), uz1 = dmin2(pm[cu1], pp[cu1]);
+            const double f0 = __dmul_rn(pc[cf0], a.h), f1 = __dmul_rn(pc[cf1], a.h);
+            double n0, n1;
+            local_solve_x2(ux0, uy0, uz0, f0, ux1, uy1, uz1, f1, n0, n1);
             if (do0 && n0 < c0) U[oc + cu0] = n0;  // u = MIN(u, ubar) (fsm3d.f90:477)
             if (do1 && n1 < c1) U[oc + cu1] = n1;
             __syncwarp();
@@ -260,8 +266,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             // slot l - 3 is final now: write its nodes back (32-byte sectors, one per lane quad)
             {
                 const int ks0 = l - 3 - kofs0, ks1 = ks0 - 4;
-                if (act0 && ks0 >= 0 && ks0 < ez) __stcg(uf + zoff(ks0) + col0, U[st_slot + cu0]);
-                if (act1 && ks1 >= 0 && ks1 < ez) __stcg(uf + zoff(ks1) + col1, U[st_slot + cu1]);
+                if (act0 && ks0 >= 0 && ks0 < ez) __stcg(pu0 + (long long)ks0 * zstride, U[st_slot + cu0]);
+                if (act1 && ks1 >= 0 && ks1 < ez) __stcg(pu1 + (long long)ks1 * zstride, U[st_slot + cu1]);
             }
             om = oc; oc = op;
             op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
@@ -281,6 +287,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             st_release_gpu(done_f + brick, (s + 1) << kProgShift);
         }
         __syncwarp();
+        if (a.stats && lane == 0) {
+            const long long t_end = clock64();
+            atomicAdd(a.stats + 0, (unsigned long long)(t_deps - t_start));   // ticket + coarse dependency wait
+            atomicAdd(a.stats + 1, (unsigned long long)t_upwind);             // fine-grained upwind waits
+            atomicAdd(a.stats + 2, (unsigned long long)(t_end - t_deps));     // everything else (incl. upwind waits)
+            atomicAdd(a.stats + 3, 1ULL);
+        }
     }
 }
 

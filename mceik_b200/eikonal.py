@@ -82,7 +82,7 @@ class EikonalSolver:
     one grid per call.  Geometry / solver parameters follow ``solverParametersType``
     (module.F90:117-131)."""
 
-    def __init__(self, ctx, nx, ny, nz, h, x0=0.0, y0=0.0, z0=0.0, tol=1e-6, maxit=20, algo=ALGO_TILES):
+    def __init__(self, ctx, nx, ny, nz, h, x0=0.0, y0=0.0, z0=0.0, tol=1e-6, maxit=20, algo=ALGO_BRICKS):
         self.ctx = ctx
         self.lib = _lib.load()
         self.grid = FsmGrid(int(nx), int(ny), int(nz), float(h), float(x0), float(y0), float(z0), float(tol), int(maxit))

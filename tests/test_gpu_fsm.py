@@ -147,3 +147,14 @@ def test_homogeneous_tables(gpu_ctx):
     t = E.compute_homogeneous_traveltimes(nx, ny, nz, 0.0, 0.0, 0.0, 1000.0, 1000.0, 1000.0, 7000.0, 12000.0, 25000.0, 2000.0)
     ref = O.homogeneous_traveltimes(nx, ny, nz, 0.0, 0.0, 0.0, 1000.0, 1000.0, 1000.0, 7000.0, 12000.0, 25000.0, 2000.0)
     assert np.array_equal(t, ref)
+
+
+def test_solver_building_blocks_selftest(gpu_ctx):
+    """sqrt_fast == __dsqrt_rn and the straight-line solver == the reference-ordered solver, bit for
+    bit, on 4e8 pseudo-random inputs each (incl. exact squares, ties and u_nan neighbours)."""
+    import ctypes as C
+    from mceik_b200 import _lib
+    b1, b2 = C.c_longlong(-1), C.c_longlong(-1)
+    for seed in (1, 2):
+        rc = _lib.load().mceik_selftest_solver(gpu_ctx.handle, seed, 200_000_000, C.byref(b1), C.byref(b2))
+        assert rc == 0 and b1.value == 0 and b2.value == 0, (b1.value, b2.value)
