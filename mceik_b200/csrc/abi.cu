@@ -336,11 +336,15 @@ int locate_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_pic
     DeviceGuard dg(ctx->device);
     cudaStream_t st = ctx->stream;
     const size_t np = std::max(nobs_total, 1);
-    double *d_w = static_cast<double *>(ctx->ws_gs_w.ensure(align_up(sizeof(double) * np) * 2 + sizeof(int) * nevents));
+    const int nblk_all = (nevents + gs::kEventsPerBlock - 1) / gs::kEventsPerBlock;
+    double *d_w = static_cast<double *>(ctx->ws_gs_w.ensure(align_up(sizeof(double) * np) * 2 + align_up(sizeof(int) * nevents) +
+                                                            sizeof(int) * nblk_all));
     double *d_w0 = d_w;
     double *d_w1 = reinterpret_cast<double *>(reinterpret_cast<char *>(d_w) + align_up(sizeof(double) * np));
     int *d_nuse = reinterpret_cast<int *>(reinterpret_cast<char *>(d_w) + 2 * align_up(sizeof(double) * np));
+    int *d_uniform = reinterpret_cast<int *>(reinterpret_cast<char *>(d_nuse) + align_up(sizeof(int) * nevents));
     gs::launch_prepare(nevents, d_obs_ptr, d_table_id, d_varobs, d_w0, d_w1, d_nuse, st);
+    gs::launch_classify(nevents, d_obs_ptr, d_table_id, d_uniform, st);
     const int max_events_per_launch = 65535 * gs::kEventsPerBlock;
     for (int e0 = 0; e0 < nevents; e0 += max_events_per_launch) {
         const int ne = std::min(max_events_per_launch, nevents - e0);
@@ -349,6 +353,7 @@ int locate_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_pic
         a.tables = ctx->d_tables;
         a.obs_ptr = d_obs_ptr + e0; a.table_id = d_table_id; a.tobs_cor = d_tobs_cor; a.w_t0 = d_w0; a.w_obj = d_w1;
         a.tori = d_tori ? d_tori + e0 : nullptr;
+        a.blk_uniform = d_uniform + e0 / gs::kEventsPerBlock;
         a.nlanes = gs::locate_lanes(ne, ctx->ngrd);
         a.partials = static_cast<gs::Partial *>(ctx->ws_gs_part.ensure(sizeof(gs::Partial) * (size_t)ne * a.nlanes));
         gs::launch_locate(a, st);

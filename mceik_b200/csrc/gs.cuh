@@ -36,6 +36,7 @@ struct LocateArgs {
     const double *w_t0;      // [npicks] (1/var)/sum(1/var)
     const double *w_obj;     // [npicks] (1/var)*sqrt2i
     const double *tori;      // [nevents] (job 1)
+    const int *blk_uniform;  // [ceil(nevents/8)] 1 = every pick slot of the block uses one table (fast kernel)
     Partial *partials;       // [nevents][nlanes]
     int nlanes;              // gridDim.x of the main kernel
 };
@@ -44,6 +45,8 @@ struct LocateArgs {
 // w_t0 = (1/var)/xnorm (locate.c:399), w_obj = (1/var)*0.7071067811865475 (locate.c:500).
 void launch_prepare(int nevents, const int *d_obs_ptr, const int *d_table_id, const double *d_varobs,
                     double *d_w_t0, double *d_w_obj, int *d_nuse, cudaStream_t st);
+// blk_uniform[b] = 1 when the 8 events of block b use the same table in every pick slot
+void launch_classify(int nevents, const int *d_obs_ptr, const int *d_table_id, int *d_blk_uniform, cudaStream_t st);
 size_t locate_smem_bytes(int maxpicks);
 int locate_lanes(int nevents, int ngrd);
 void launch_locate(const LocateArgs &a, cudaStream_t st);
