@@ -4,10 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...   (the reference's CPU path, rank 0 only)
 
-A *step* is one pass of the eikonal hot path over one batch of synthetic input: the per-GPU shard
-of BASELINE config 3 -- 16 station fields on the 256^3 checkerboard model, solved to convergence
+A *step* is one pass of the eikonal hot path over one batch of synthetic input: BASELINE config 3
+-- 64 stations x (P, S) = 128 fields on the 256^3 checkerboard model -- solved to convergence
 (fill + boundary conditions + all sweeps + convergence tests), packed to fp32 tables and, for
-N > 1, all-gathered over NCCL.  Weak scaling: every rank owns 16 fields.
+N > 1, all-gathered over NCCL.  Strong scaling: the 128 fields are sharded over the N ranks
+(contiguous blocks, so a rank holds P fields, S fields or, for N = 1, both models).
 `value` = node-updates of all ranks / max-over-ranks device time, inputs resident in HBM.
 `e2e`   = the same through the host-pointer C-ABI call (mceik_fsm_solve_batched_host): pinned
           host slowness in, fp64 fields out, copies inside the timed region.
@@ -33,7 +34,7 @@ import cases  # noqa: E402
 
 GRID = 256
 H = 1000.0
-FIELDS_PER_GPU = 16
+TOTAL_FIELDS = 128  # 64 stations x (P, S)
 NSTATIONS = 64
 BYTES_PER_UPDATE = 24  # fp64 read u, write u, read slow
 METRIC = "eikonal_node_updates_per_s"
@@ -47,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID, help=argparse.SUPPRESS)
-    ap.add_argument("--fields", type=int, default=FIELDS_PER_GPU, help=argparse.SUPPRESS)
+    ap.add_argument("--fields", type=int, default=TOTAL_FIELDS, help=argparse.SUPPRESS)  # total over all ranks
     ap.add_argument("--gs-events", type=int, default=256, help="events per GPU per grid-search step")
     ap.add_argument("--gs-stations", type=int, default=128, help=argparse.SUPPRESS)
     ap.add_argument("--skip-gs", action="store_true", help=argparse.SUPPRESS)
@@ -56,18 +57,25 @@ def parse():
 
 
 def workload_config(a, n_gpus):
-    return {"workload": f"BASELINE config 3 per-GPU shard: fsm3d batched, {a.fields} station fields/GPU on "
-                        f"{a.grid}^3 checkerboard velocity (+-10%, 32-node cells), P model on ranks < ceil(N/2) else S, "
-                        f"tol 1e-6, maxit 20, solved to convergence + fp32 table pack"
+    per = a.fields // n_gpus
+    return {"workload": f"BASELINE config 3: fsm3d batched, {a.fields // 2} stations x (P,S) = {a.fields} fields on "
+                        f"{a.grid}^3 checkerboard velocity (+-10%, 32-node cells; vs = vp/sqrt3), tol 1e-6, maxit 20, "
+                        f"solved to convergence + fp32 table pack"
                         + (" + NCCL all-gather of tables" if n_gpus > 1 else ""),
-            "fields_per_gpu": a.fields, "grid": [a.grid] * 3, "sharding": f"sources x{n_gpus}",
-            "l2": f"inputs larger than L2: {a.fields * a.grid ** 3 * 8 / 1e9:.1f} GB of fp64 fields per GPU"}
+            "fields_total": a.fields, "fields_per_gpu": per, "grid": [a.grid] * 3,
+            "sharding": f"sources sharded x{n_gpus} (contiguous blocks: P fields first, then S)",
+            "l2": f"inputs larger than L2: {per * a.grid ** 3 * 8 / 1e9:.1f} GB of fp64 fields per GPU"}
 
 
-def rank_sources(a, rank):
-    xs, ys, zs = cases.interior_sources(NSTATIONS, a.grid, a.grid, a.grid, H, seed=3)
-    idx = (rank * a.fields + np.arange(a.fields)) % NSTATIONS
-    return xs[idx], ys[idx], zs[idx]
+def rank_fields(a, rank, world):
+    """Global field ids of this rank: field f < fields/2 is station f with the P model, else station
+    f - fields/2 with the S model.  Returns (station xs, ys, zs, model id per field)."""
+    from mceik_b200 import sharding
+    ids = sharding.shard_fields(a.fields, world, rank)
+    half = a.fields // 2
+    xs, ys, zs = cases.interior_sources(max(half, 1), a.grid, a.grid, a.grid, H, seed=3)
+    st = ids % max(half, 1)
+    return xs[st], ys[st], zs[st], (ids >= half).astype(np.int32)
 
 
 def measured_peak():
@@ -139,7 +147,7 @@ def cpu_fsm_sample(a):
     import oracle_lib as O
     n = a.grid
     slow = cases.checkerboard_slowness(n, n, n, cell=32)
-    xs, ys, zs = rank_sources(a, 0)
+    xs, ys, zs, _ = rank_fields(a, 0, 1)
     cores = os.cpu_count() or 1
     t = time.time()
     u, ierr, it = O.eikonal_serial(n, n, n, H, slow, 0.0, xs[0], ys[0], zs[0], tol=1e-6, maxit=20)
@@ -164,7 +172,7 @@ def run_reference(a):
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, a.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,7 +225,6 @@ def run_ours(a):
     ctx = mceik_b200.Context(local, stream=stream.cuda_stream)
     n = a.grid
     N = n ** 3
-    nf = a.fields
 
     def barrier():
         if world > 1:
@@ -239,12 +246,14 @@ def run_ours(a):
         return float(t.item())
 
     # ---------------- eikonal: device-resident step ----------------
-    is_s = world > 1 and rank >= (world + 1) // 2
-    slow_h = torch.from_numpy(cases.checkerboard_slowness(n, n, n, cell=32, vs=is_s)).pin_memory()
+    if a.fields % world:
+        raise SystemExit("--fields must be a multiple of --gpus")
+    xs, ys, zs, fmodel = rank_fields(a, rank, world)
+    nf = len(xs)
+    slow_h = torch.from_numpy(np.stack([cases.checkerboard_slowness(n, n, n, cell=32, vs=False),
+                                        cases.checkerboard_slowness(n, n, n, cell=32, vs=True)])).pin_memory()
     d_slow = slow_h.cuda()
-    xs, ys, zs = rank_sources(a, rank)
     ts = np.zeros(nf)
-    fmodel = np.zeros(nf, np.int32)
     d_u = torch.empty((nf, N), dtype=torch.float64, device="cuda")
     d_tab = torch.empty((nf, N), dtype=torch.float32, device="cuda")
     d_all = torch.empty((world * nf, N), dtype=torch.float32, device="cuda") if world > 1 else None
@@ -278,12 +287,13 @@ def run_ours(a):
     dt_ms = max_over_ranks(e0.elapsed_time(e1))
     tot_updates = sum_over_ranks(float(updates))
     value = tot_updates / (dt_ms * 1e-3) / 1e9
-    iters = [int(i) for i in sol.last_iters]
+    li = np.asarray(sol.last_iters)
+    iters = {"min": int(li.min()), "max": int(li.max()), "mean": float(li.mean())}
     peak, peak_src = measured_peak()
     sweep_updates = updates  # every node-update of the solve happens inside the sweep kernel
     ach = BYTES_PER_UPDATE * sweep_updates / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "sweep_tiles_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if ach else None, "traffic": ncu_traffic("sweep_tiles_kernel"),
+    roofline = {"bound": "hbm", "kernel": "sweep_bricks_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak if ach else None, "traffic": ncu_traffic("sweep_bricks_kernel"),
                 "peak_source": peak_src, "launches": sweep_launches,
                 "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                 "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * sweep_updates / max(sweep_launches, 1),
@@ -291,14 +301,14 @@ def run_ours(a):
 
     # ---------------- eikonal: end-to-end through the host-pointer C ABI ----------------
     u_h = torch.empty((nf, N), dtype=torch.float64).pin_memory()
-    slow_np = slow_h.numpy().reshape(1, N)
+    slow_np = slow_h.numpy().reshape(2, N)
     sp = np.arange(nf + 1, dtype=np.int32)
     iters_h, ferr_h = np.zeros(nf, np.int32), np.zeros(nf, np.int32)
     lib = _lib.load()
     P = lambda x, t: x.ctypes.data_as(t)
 
     def e2e_step():
-        rc = lib.mceik_fsm_solve_batched_host(ctx.handle, C.byref(sol.grid), 1, P(slow_np, _lib.c_dbl_p), nf,
+        rc = lib.mceik_fsm_solve_batched_host(ctx.handle, C.byref(sol.grid), 2, P(slow_np, _lib.c_dbl_p), nf,
                                               P(fmodel, _lib.c_int_p), P(sp, _lib.c_int_p), P(ts, _lib.c_dbl_p),
                                               P(xs, _lib.c_dbl_p), P(ys, _lib.c_dbl_p), P(zs, _lib.c_dbl_p),
                                               C.cast(u_h.data_ptr(), _lib.c_dbl_p), None, 0, P(iters_h, _lib.c_int_p),
@@ -315,7 +325,7 @@ def run_ours(a):
     barrier()
     e2e_dt = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": sum_over_ranks(float(e2e_updates)) / e2e_dt / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": int(N * 8 + 4 * 8 * nf), "d2h_bytes_per_step": int(nf * N * 8),
+           "h2d_bytes_per_step": int(2 * N * 8 + 4 * 8 * nf), "d2h_bytes_per_step": int(nf * N * 8),
            "api": "mceik_fsm_solve_batched_host (pinned host slowness in, fp64 fields out)"}
     del u_h
 
@@ -331,7 +341,7 @@ def run_ours(a):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": dt_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dt_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": dict(workload_config(a, world), iterations_per_field=iters),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "events": events}
@@ -405,8 +415,8 @@ def run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, d_u, d_
     alg_bytes = nuse * N * 4 * steps  # each needed fp32 table value once per event
     peak, peak_src = measured_peak()
     ach = alg_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "locate_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic("locate_kernel"), "peak_source": peak_src,
+    roof = {"bound": "hbm", "kernel": "locate_uniform_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": ncu_traffic("locate_uniform_kernel"), "peak_source": peak_src,
             "fp64_tflops": 8.0 * nuse * N * steps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
             "note": "tables are reused across the 8 events of a CTA, so the binding limit is the fp64 pipe "
                     "(8 non-fused flops per event x pick x node), not HBM; frac may exceed 1"}
