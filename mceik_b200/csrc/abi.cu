@@ -50,7 +50,7 @@ struct mceik_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     fsm::TilePlan plan;
     fsm::BrickPlan bplan;
-    int brick_zc = 64;
+    int brick_zc = 64, brick_by = 8;
     // eikonal workspaces
     DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
     // locator state
@@ -140,7 +140,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     ctx->plan.build(nx, ny, nz, st);
     const fsm::TilePlan &pl = ctx->plan;
     const bool bricks = ctx->fsm_algo == MCEIK_FSM_ALGO_BRICKS;
-    if (bricks) ctx->bplan.build(nx, ny, nz, ctx->brick_zc, st);
+    if (bricks) ctx->bplan.build(nx, ny, nz, ctx->brick_by, ctx->brick_zc, st);
     const fsm::BrickPlan &bp = ctx->bplan;
 
     // ---- boundary conditions: stencil records per field (host), unique node lists per field
@@ -228,8 +228,12 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             const int *d_active = upload(ctx->ws_meta, o_active, active, st);
             fsm::BrickArgs a;
             a.nx = nx; a.ny = ny; a.nz = nz;
-            a.nbx = bp.nbx; a.nby = bp.nby; a.nbz = bp.nbz; a.nbricks = bp.nbricks; a.nblevels = bp.nblevels; a.zc = bp.zc;
+            a.nbx = bp.nbx; a.nby = bp.nby; a.nbz = bp.nbz; a.nbricks = bp.nbricks; a.nblevels = bp.nblevels; a.zc = bp.zc; a.by = bp.by;
             a.nfields_active = (int)active.size();
+            // few fields: short publication interval (tight pipelining of the brick wavefront);
+            // many fields: parallelism is plentiful, publish rarely (each publication costs a fence)
+            a.publish = active.size() >= 64 ? 32 : (active.size() >= 32 ? 16 : 8);
+            if (const char *e = getenv("MCEIK_FSM_PUBLISH")) a.publish = atoi(e);
             a.h = g->h;
             a.active = d_active; a.field_model = d_fmodel; a.slow = d_slow; a.u = d_u;
             a.brick_order = ctx->bplan.brick_order.as<int>();
@@ -452,6 +456,7 @@ int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
     if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS && algo != MCEIK_FSM_ALGO_BRICKS)) return -1;
     c->fsm_algo = algo;
     if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(64, atoi(e)));
+    if (const char *e = getenv("MCEIK_FSM_BY")) c->brick_by = atoi(e) == 16 ? 16 : 8;
     return 0;
 }
 long long mceik_fsm_last_node_updates(mceik_ctx *c) { return c ? c->last_updates : 0; }

@@ -62,19 +62,20 @@ struct SweepArgs {
 
 // Brick decomposition (8 x 8 x zc nodes) used by the streaming sweep kernel (fsm_bricks.cu).
 struct BrickPlan {
-    int nx = 0, ny = 0, nz = 0, zc = 0;
+    int nx = 0, ny = 0, nz = 0, zc = 0, by = 0;  // brick = 8 x by x zc nodes (by = 8 or 16)
     int nbx = 0, nby = 0, nbz = 0, nbricks = 0, nblevels = 0;
     DevBuf brick_order;  // int[nbricks]: I | J<<10 | K<<20 sorted by I+J+K
     DevBuf blevel_ptr;   // int[nblevels+1]
-    void build(int nx_, int ny_, int nz_, int zc_, cudaStream_t st);
+    void build(int nx_, int ny_, int nz_, int by_, int zc_, cudaStream_t st);
     void release();
 };
 
 // Arguments of one launch of the brick sweep kernel (= 8 sweeps of every active field).
 struct BrickArgs {
     int nx, ny, nz;
-    int nbx, nby, nbz, nbricks, nblevels, zc;
+    int nbx, nby, nbz, nbricks, nblevels, zc, by;
     int nfields_active;
+    int publish;              // a sweeping warp publishes its progress every `publish` steps (8, 16 or 32)
     double h;
     const int *active;        // [nfields_active] field ids
     const int *field_model;   // [nfields]
@@ -89,7 +90,6 @@ struct BrickArgs {
     unsigned long long *stats;    // optional [4] cycle counters (MCEIK_FSM_STATS=1), else nullptr
 };
 void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
-size_t bricks_smem_bytes();
 
 // device self-test of sqrt_fast / local_solve_sl against __dsqrt_rn / local_solve; d_bad[2] counts mismatches
 void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st);

@@ -4,15 +4,15 @@
 // updates upwind neighbours first reproduces the reference's hyperplane order bit for bit,
 // fsm3d.f90:62-85, 419-456), different mapping to the machine:
 //
-//   * A task is one WARP walking one brick (8 x 8 nodes in cross-section, zc nodes long) of one
-//     field for one sweep.  Lane (i, jq) owns the columns (i, jq) and (i, jq+4) of the cross-
-//     section and marches along the brick axis: at step l it updates the nodes i + j + k = l, so a
-//     full hyperplane of the brick (64 nodes, 2 independent updates per lane) is in flight every
-//     step and there is no block-wide barrier anywhere -- only __syncwarp().
+//   * A task is one WARP walking one brick (8 x 8 nodes in cross-section -- 8 x 16 as an option --
+//     zc nodes long) of one field for one sweep.  Lane (i, q) owns the columns (i, 2q), (i, 2q+1) of
+//     the cross-section and marches along the brick axis: at step l it updates the nodes
+//     i + j + k = l, so a full hyperplane of the brick (64 nodes, 2 independent updates per lane) is
+//     in flight every step and there is no block-wide barrier anywhere -- only __syncwarp().
 //   * The brick streams through a per-warp shared-memory ring of 11 skewed planes (10x10 travel-
 //     time cells + 8x8 slowness cells each) filled by cp.async two slots ahead in 32-byte sectors,
 //     updated in place, and written back as soon as a slot is final.  Nothing but the ring is ever
-//     staged, so loads, the 2 x 64 Godunov updates per step and stores overlap continuously, and
+//     staged, so loads, the 64 Godunov updates per step and stores overlap continuously, and
 //     15 warps (one brick each) are resident per SM.
 //   * Bricks form the same DAG as tiles; a persistent grid of independent warps pulls tickets in a
 //     topological order and spins on per-(field, brick) completion counters.
@@ -26,23 +26,28 @@ namespace fsm {
 
 namespace {
 
-constexpr int kBx = 8, kBy = 8;          // brick cross-section (nodes)
+constexpr int kBx = 8;                   // brick cross-section: kBx x (4 * NC) nodes, NC columns per lane
 constexpr int kPrefetch = 2;             // ring slots loaded ahead of their first reader
 constexpr int kRing = 9 + kPrefetch;     // ring depth in slots (see "ring" below)
 constexpr int kURow = kBx + 2;           // cell row stride inside a slot (doubles), halo included
-constexpr int kUCells = kURow * (kBy + 2);
-constexpr int kSlot = kUCells + kBx * kBy;  // one slot: 10x10 travel-time cells + 8x8 slowness cells
 constexpr int kMaxZc = 64;               // longest brick (mask storage)
-constexpr int kWarpsPerCta = 15;
 // Progress word of a (field, brick): (sweeps completed << kProgShift) while idle, and
 // (sweep << kProgShift) + steps completed while the brick is being swept.
 constexpr int kProgShift = 12;
-constexpr int kPublish = 8;     // a sweeping warp publishes its progress every kPublish steps
-// A brick may run kLead steps behind its upwind x / y neighbours: the halo node it loads at step l
-// is in ring slot M = l + 4 + prefetch, and the neighbour wrote it back by its step M + 11 (y face;
-// M + 5 for the x face): the neighbour must have completed M + 12 steps.
-constexpr int kLead = 11;
-constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc;
+// A brick may run behind its upwind x / y neighbours: the halo node it loads at step l is in ring
+// slot M = l + 4 + prefetch, and the neighbour wrote it back by its step M + By + 3 (y face; M + 5
+// for the x face): the neighbour must have completed M + By + 4 steps (BrickCfg::kLead = By + 3).
+
+template <int NC> struct BrickCfg {
+    static constexpr int kBy = 4 * NC;
+    static constexpr int kUCells = kURow * (kBy + 2);
+    static constexpr int kSlot = kUCells + kBx * kBy;   // one slot: travel-time cells (with halo) + slowness cells
+    static constexpr int kHalo = 2 * kBy + 2 * kBx;     // halo cells per slot
+    static constexpr int kMaskWords = (kBx * kBy + 63) / 64;
+    static constexpr int kWarps = NC == 2 ? 15 : 8;
+    static constexpr int kLead = kBy + 3;
+    static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc * kMaskWords;
+};
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -57,45 +62,66 @@ __device__ __forceinline__ int xgroup(int i) { return (i + 4) >> 2; }
 
 }  // namespace
 
-// The ring.  Cell (i, j, k) of the brick (halo: i, j in [-1, 8], k in [-1, ez]) lives in ring slot
+// The ring.  Cell (i, j, k) of the brick (halo: i in [-1, 8], j in [-1, By], k in [-1, ez]) lives in
+// ring slot
 //     m = xgroup(i) + (j + 1) + (k + 1)        (mod kRing)
-// at cell offset (j+1)*10 + (i+1): a slot is a *skewed* plane made of sixteen 4-node x-sectors, one
-// per (x-group, j), so that global traffic stays sector-granular (32 B) while a slot only lives
-// from the step its first node is read to the step its last node is final: the node (i, j, k)
-// is updated at step l = i + j + k, i.e. in slot l + c with c = xgroup(i) - i + 2 in [-3, 3], and
-// reads slots m-1, m, m+1 only.  Slot m is first read at step m-4, last written at step m+3 and
-// last read at step m+4, so kRing = 9 + prefetch slots suffice (19 planes would be needed without
-// the skew), which is what lets 15 independent warps share one SM's shared memory.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(const BrickArgs a) {
+// at cell offset (j+1)*10 + (i+1): a slot is a *skewed* plane made of 4-node x-sectors, one per
+// (x-group, j), so that global traffic stays sector-granular (32 B) while a slot only lives from the
+// step its first node is read to the step its last node is final: the node (i, j, k) is updated at
+// step l = i + j + k, i.e. in slot l + c with c = xgroup(i) - i + 2 in [-3, 3] (independent of j, so
+// the cross-section can be widened in y for free), and reads slots m-1, m, m+1 only.  Slot m is
+// first read at step m-4, last written at step m+3 and last read at step m+4, so kRing = 9 +
+// prefetch slots suffice (By + 9 + prefetch planes would be needed without the skew).
+//
+// A lane owns NC columns (li, NC*q .. NC*q + NC-1), q = lane & 3, li = lane >> 2: NC independent
+// Godunov updates per step whose instruction streams the compiler interleaves.  The z-neighbours of
+// a column never leave the lane: the value read ahead as zp becomes `self` one step later and the
+// lane's own result becomes zm.
+template <int NC>
+__global__ void __launch_bounds__(BrickCfg<NC>::kWarps * 32, 1) sweep_bricks_kernel(const BrickArgs a) {
+    using Cfg = BrickCfg<NC>;
+    constexpr int kBy = Cfg::kBy, kUCells = Cfg::kUCells, kSlot = Cfg::kSlot, kMaskWords = Cfg::kMaskWords;
+    constexpr int kHaloPerLane = (Cfg::kHalo + 31) / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
-    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc]
+    double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * Cfg::kWarpSmem);  // [kRing][kSlot]
+    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc][kMaskWords]
 
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const size_t nxy = (size_t)nx * ny, N = nxy * nz;
     const int nf = a.nfields_active;
     const long long per_sweep = (long long)a.nbricks * nf;
     const long long ntasks = 8 * per_sweep;
-    const int li = lane & 7, jq = lane >> 3;  // lane -> columns (li, jq) and (li, jq + 4)
+    const int li = lane >> 2, j0 = NC * (lane & 3);
     const int ig = xgroup(li);
-    // this lane's halo cell: lanes 0-7: (i=-1, j=lane); 8-15: (i=8, j); 16-23: (i, j=-1); 24-31: (i, j=8)
-    int hi_i, hi_j;
-    if (lane < 8) { hi_i = -1; hi_j = lane; }
-    else if (lane < 16) { hi_i = kBx; hi_j = lane - 8; }
-    else if (lane < 24) { hi_i = lane - 16; hi_j = -1; }
-    else { hi_i = lane - 24; hi_j = kBy; }
-    const int cu0 = (jq + 1) * kURow + (li + 1), cu1 = (jq + 5) * kURow + (li + 1);  // cell offsets in a slot
-    const int cuh = (hi_j + 1) * kURow + (hi_i + 1);
-    const int cf0 = kUCells + jq * kBx + li, cf1 = kUCells + (jq + 4) * kBx + li;
-    const int kofs0 = ig + jq + 2, kofsh = xgroup(hi_i) + hi_j + 2;  // k = m - kofs (second column: kofs0 + 4)
+    // halo cells of this lane: cell h = lane + 32*t: [0, By): (i=-1, j=h); [By, 2By): (i=8, j=h-By);
+    // then (i = h', j = -1) for 8 cells and (i = h'', j = By) for 8 cells
+    int cuh[kHaloPerLane], kofsh[kHaloPerLane], hi_i[kHaloPerLane], hi_j[kHaloPerLane];
+#pragma unroll
+    for (int t = 0; t < kHaloPerLane; ++t) {
+        const int h = lane + 32 * t;
+        int hi, hj;
+        if (h < kBy) { hi = -1; hj = h; }
+        else if (h < 2 * kBy) { hi = kBx; hj = h - kBy; }
+        else if (h < 2 * kBy + kBx) { hi = h - 2 * kBy; hj = -1; }
+        else { hi = h - 2 * kBy - kBx; hj = kBy; }
+        if (h >= Cfg::kHalo) { hi = 0; hj = 0; }
+        hi_i[t] = hi; hi_j[t] = hj;
+        cuh[t] = (hj + 1) * kURow + (hi + 1);
+        kofsh[t] = (h < Cfg::kHalo) ? xgroup(hi) + hj + 2 : (1 << 20);  // k = m - kofs (never valid when unused)
+    }
+    const int cu0 = (j0 + 1) * kURow + (li + 1);        // cell offset of column c: cu0 + c * kURow
+    const int cf0 = kUCells + j0 * kBx + li;            // slowness cell of column c: cf0 + c * kBx
+    const int kofs0 = ig + j0 + 2;                      // k of column c in slot m: m - kofs0 - c
     const bool xm_prev = (li & 3) == 0, xp_next = (li & 3) == 3;  // x-neighbour in the previous / next slot
+    const int publish = a.publish;  // steps between progress publications (power of two)
 
     while (true) {
         long long t = 0;
         if (lane == 0) t = (long long)atomicAdd(a.queue, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= ntasks) break;
+        const long long t_start = a.stats ? clock64() : 0;
 
         // ---- ticket -> (sweep, brick level, brick, field); order [sweep][brick level][brick][field]
         const int s = (int)(t / per_sweep);
@@ -117,10 +143,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
         const int brick = (K * a.nby + J) * a.nbx + I;
         int *done_f = a.done + (size_t)f * a.nbricks;
 
-        const long long t_start = a.stats ? clock64() : 0;
         // ---- dependencies (coarse): this brick and its 6 neighbours finished sweep s-1; the upwind z
         //      neighbour finished sweep s.  The upwind x / y neighbours only need a kLead-step head
-        //      start, which is checked every kPublish steps inside the sweep loop (fine-grained
+        //      start, which is checked every `publish` steps inside the sweep loop (fine-grained
         //      pipelining of the brick wavefront).
         const int *up_ptr = nullptr;  // lanes 0 / 1: progress word of the upwind x / y neighbour
         if (lane < 7) {
@@ -151,7 +176,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             if (a.stats) t_upwind += clock64() - t0;
         };
         const long long t_deps = a.stats ? clock64() : 0;
-        wait_upwind(4 + kPrefetch + kLead);  // the prologue issues slots 0 .. 3 + kPrefetch
+        wait_upwind(4 + kPrefetch + Cfg::kLead);  // the prologue issues slots 0 .. 3 + kPrefetch
         __syncwarp();
 
         // brick extent in memory coordinates and the sweep-oriented local frame:
@@ -178,29 +203,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
             }
             hasbc = __any_sync(0xffffffffu, mine);
             if (hasbc) {
-                for (int k = lane; k < kMaxZc; k += 32) bcm[k] = 0ULL;
+                for (int k = lane; k < kMaxZc * kMaskWords; k += 32) bcm[k] = 0ULL;
                 __syncwarp();
                 for (int n = b0 + lane; n < b1; n += 32) {
                     const int node = __ldg(a.bc_node + n);
                     const int gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
                     if (gx >= x_lo && gx <= x_hi && gy >= y_lo && gy <= y_hi && gz >= z_lo && gz <= z_hi) {
                         const int i = (gx - xb) * sx, j = (gy - yb) * sy, k = (gz - zb) * sz;
-                        atomicOr(bcm + k, 1ULL << (j * kBx + i));
+                        const int bit = j * kBx + i;
+                        atomicOr(bcm + k * kMaskWords + (bit >> 6), 1ULL << (bit & 63));
                     }
                 }
                 __syncwarp();
             }
         }
 
-        // per-lane base pointers (plane k = 0) of its two interior columns and of its halo column;
+        // per-lane base pointers (plane k = 0) of its interior columns and of its halo columns;
         // plane k sits at base + kclamp(k) * zstride, where kclamp folds the two z-halo planes
         // (k = -1, k = ez) back onto the boundary plane when the brick touches the grid boundary.
         const int gxi = min(max(xb + sx * li, 0), nx - 1);
-        const size_t col0 = (size_t)zb * nxy + (size_t)min(max(yb + sy * jq, 0), ny - 1) * nx + gxi;
-        const size_t col1 = (size_t)zb * nxy + (size_t)min(max(yb + sy * (jq + 4), 0), ny - 1) * nx + gxi;
-        const size_t colh = (size_t)zb * nxy + (size_t)min(max(yb + sy * hi_j, 0), ny - 1) * nx + min(max(xb + sx * hi_i, 0), nx - 1);
-        double *pu0 = uf + col0, *pu1 = uf + col1;
-        const double *puh = uf + colh, *pf0 = sl + col0, *pf1 = sl + col1;
+        double *pu[NC];
+        const double *pf[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const size_t col = (size_t)zb * nxy + (size_t)min(max(yb + sy * (j0 + c), 0), ny - 1) * nx + gxi;
+            pu[c] = uf + col;
+            pf[c] = sl + col;
+        }
+        const double *puh[kHaloPerLane];
+#pragma unroll
+        for (int t2 = 0; t2 < kHaloPerLane; ++t2)
+            puh[t2] = uf + (size_t)zb * nxy + (size_t)min(max(yb + sy * hi_j[t2], 0), ny - 1) * nx +
+                      min(max(xb + sx * hi_i[t2], 0), nx - 1);
         const long long zstride = (long long)sz * (long long)nxy;
         const int klo = (zb - sz < 0 || zb - sz > nz - 1) ? 0 : -1;             // plane index used for k = -1
         const int khi = (zb + sz * ez < 0 || zb + sz * ez > nz - 1) ? ez - 1 : ez;  // ... and for k = ez
@@ -209,70 +243,105 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
         int ld_m = 0;
         auto issue_slot = [&]() {
             double *sp = U + ld_slot;
-            const int k0 = ld_m - kofs0, k1 = k0 - 4, kh = ld_m - kofsh;
-            if (k0 >= -1 && k0 <= ez) {
-                const long long z = (long long)min(max(k0, klo), khi) * zstride;
-                cp_async8(sp + cu0, pu0 + z);
-                if (k0 >= 0 && k0 < ez) cp_async8(sp + cf0, pf0 + z);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int k = ld_m - kofs0 - c;
+                if (k >= -1 && k <= ez) {
+                    const long long z = (long long)min(max(k, klo), khi) * zstride;
+                    cp_async8(sp + cu0 + c * kURow, pu[c] + z);
+                    if (k >= 0 && k < ez) cp_async8(sp + cf0 + c * kBx, pf[c] + z);
+                }
             }
-            if (k1 >= -1 && k1 <= ez) {
-                const long long z = (long long)min(max(k1, klo), khi) * zstride;
-                cp_async8(sp + cu1, pu1 + z);
-                if (k1 >= 0 && k1 < ez) cp_async8(sp + cf1, pf1 + z);
+#pragma unroll
+            for (int t2 = 0; t2 < kHaloPerLane; ++t2) {
+                const int kh = ld_m - kofsh[t2];
+                if (kh >= 0 && kh < ez) cp_async8(sp + cuh[t2], puh[t2] + (long long)kh * zstride);
             }
-            if (kh >= 0 && kh < ez) cp_async8(sp + cuh, puh + (long long)kh * zstride);
             cp_async_commit();
             ++ld_m;
             ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
         };
         for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot();
 
-        const bool act0 = li < ex && jq < ey, act1 = li < ex && jq + 4 < ey;
-        // slot offsets of the node this lane updates at step l: m = l + c, c = ig - li + 2
-        int mc = ig - li + 2;                       // slot number at l = 0 (may be negative)
+        bool act[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) act[c] = li < ex && j0 + c < ey;
+        // slot offsets of the nodes this lane updates at step l: m = l + cofs, cofs = ig - li + 2
+        const int mc = ig - li + 2;                 // slot number at l = 0 (may be negative)
         int oc = ((mc % kRing) + kRing) % kRing * kSlot;
         int om = (oc == 0) ? (kRing - 1) * kSlot : oc - kSlot;
         int op = (oc + kSlot == kRing * kSlot) ? 0 : oc + kSlot;
         int st_slot = ((-3 % kRing) + kRing) % kRing * kSlot;  // slot l - 3 at l = 0
-        const int nsteps = ez + 14;
+
+        // z-neighbour registers of every column: self = u(k) before its update, zm = u(k-1) after its
+        // update.  Columns that start at k = 0 or k = -1 at step 0 take them from the ring (slots <= 4
+        // have landed); the others pick them up on their way (zp read at k = -2, -1).
+        cp_async_wait<kPrefetch - 1>();
+        __syncwarp();
+        double self[NC], zm[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int k = -li - j0 - c;  // k of column c at step 0
+            self[c] = 0.0; zm[c] = 0.0;
+            if (k == 0) {
+                self[c] = U[(ig + j0 + c + 2) * kSlot + cu0 + c * kURow];
+                zm[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
+            } else if (k == -1) {
+                self[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
+            }
+        }
+
+        const int nsteps = ez + kBy + 6;
         for (int l = 0; l < nsteps; ++l) {
-            if ((l & (kPublish - 1)) == 0) wait_upwind(l + kPublish + 4 + kPrefetch + kLead);
+            if ((l & (publish - 1)) == 0) wait_upwind(l + publish + 4 + kPrefetch + Cfg::kLead);
             issue_slot();
             cp_async_wait<kPrefetch>();  // slots <= l + 4 have landed (for this lane)
             __syncwarp();                // ... and for every lane of the warp
 
-            const int k0 = l - li - jq, k1 = k0 - 4;
-            bool do0 = act0 && k0 >= 0 && k0 < ez, do1 = act1 && k1 >= 0 && k1 < ez;
+            const int k0 = l - li - j0;  // k of column c: k0 - c
+            bool go[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) go[c] = act[c] && (unsigned)(k0 - c) < (unsigned)ez;
             if (hasbc) {
-                if (do0 && ((bcm[k0] >> (jq * kBx + li)) & 1ULL)) do0 = false;
-                if (do1 && ((bcm[k1] >> ((jq + 4) * kBx + li)) & 1ULL)) do1 = false;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const int bit = (j0 + c) * kBx + li;
+                    if (go[c] && ((bcm[(k0 - c) * kMaskWords + (bit >> 6)] >> (bit & 63)) & 1ULL)) go[c] = false;
+                }
             }
-            // Both nodes of the lane are evaluated unconditionally and side by side (two independent
-            // dependency chains for the scheduler to interleave); only the final store is predicated.
-            // An inactive node reads valid ring cells whose values are simply not used.
-            const double *pm = U + om, *pc = U + oc, *pp = U + op;
-            const double *pxm = xm_prev ? pm : pc, *pxp = xp_next ? pp : pc;
-            const double c0 = pc[cu0], c1 = pc[cu1];
-            const double ux0 = dmin2(pxm[cu0 - 1], pxp[cu0 + 1]), ux1 = dmin2(pxm[cu1 - 1], pxp[cu1 + 1]);
-            const double uy0 = dmin2(pm[cu0 - kURow], pp[cu0 + kURow]), uy1 = dmin2(pm[cu1 - kURow], pp[cu1 + kURow]);
-            const double uz0 = dmin2(pm[cu0], pp[cu0]), uz1 = dmin2(pm[cu1], pp[cu1]);
-            const double f0 = __dmul_rn(pc[cf0], a.h), f1 = __dmul_rn(pc[cf1], a.h);
-            double n0, n1;
-            local_solve_x2(ux0, uy0, uz0, f0, ux1, uy1, uz1, f1, n0, n1);
-            if (do0 && n0 < c0) U[oc + cu0] = n0;  // u = MIN(u, ubar) (fsm3d.f90:477)
-            if (do1 && n1 < c1) U[oc + cu1] = n1;
+            // All NC nodes of the lane are evaluated unconditionally and side by side; only the final
+            // store is predicated.  An inactive node reads valid ring cells whose values are not used.
+            const double *pm = U + om + cu0, *pc = U + oc + cu0, *pp = U + op + cu0;
+            const double *pxm = (xm_prev ? pm : pc) - 1, *pxp = (xp_next ? pp : pc) + 1;
+            double ux[NC], uy[NC], uz[NC], fh[NC], zp[NC], nv[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                zp[c] = pp[c * kURow];
+                ux[c] = dmin2(pxm[c * kURow], pxp[c * kURow]);
+                uy[c] = dmin2(pm[(c - 1) * kURow], pp[(c + 1) * kURow]);
+                uz[c] = dmin2(zm[c], zp[c]);
+                fh[c] = __dmul_rn(U[oc + cf0 + c * kBx], a.h);
+            }
+            local_solve_xn<NC>(ux, uy, uz, fh, nv);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const bool upd = go[c] && nv[c] < self[c];  // u = MIN(u, ubar) (fsm3d.f90:477)
+                if (upd) U[oc + cu0 + c * kURow] = nv[c];
+                zm[c] = upd ? nv[c] : self[c];
+                self[c] = zp[c];
+            }
             __syncwarp();
 
             // slot l - 3 is final now: write its nodes back (32-byte sectors, one per lane quad)
-            {
-                const int ks0 = l - 3 - kofs0, ks1 = ks0 - 4;
-                if (act0 && ks0 >= 0 && ks0 < ez) __stcg(pu0 + (long long)ks0 * zstride, U[st_slot + cu0]);
-                if (act1 && ks1 >= 0 && ks1 < ez) __stcg(pu1 + (long long)ks1 * zstride, U[st_slot + cu1]);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int ks = l - 3 - kofs0 - c;
+                if (act[c] && (unsigned)ks < (unsigned)ez) __stcg(pu[c] + (long long)ks * zstride, U[st_slot + cu0 + c * kURow]);
             }
             om = oc; oc = op;
             op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
             st_slot = (st_slot + kSlot == kRing * kSlot) ? 0 : st_slot + kSlot;
-            if (((l + 1) & (kPublish - 1)) == 0 && l + 1 < nsteps) {  // publish progress
+            if (((l + 1) & (publish - 1)) == 0 && l + 1 < nsteps) {  // publish progress
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence();
@@ -297,27 +366,33 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 1) sweep_bricks_kernel(cons
     }
 }
 
-size_t bricks_smem_bytes() { return kWarpSmem * kWarpsPerCta; }
-
-void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st) {
-    if (a.nfields_active == 0) return;
-    if (a.zc < 1 || a.zc > kMaxZc) throw CudaError("brick length out of range");
-    const size_t smem = bricks_smem_bytes();
-    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NC>
+static void launch_bricks_impl(const BrickArgs &a, cudaStream_t st) {
+    using Cfg = BrickCfg<NC>;
+    const size_t smem = Cfg::kWarpSmem * Cfg::kWarps;
+    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 0;
     MCEIK_CUDA(cudaGetDevice(&dev));
     MCEIK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     const long long ntasks = 8LL * a.nbricks * a.nfields_active;
-    const int grid = (int)std::min<long long>((ntasks + kWarpsPerCta - 1) / kWarpsPerCta, nsm);
-    sweep_bricks_kernel<<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    const int grid = (int)std::min<long long>((ntasks + Cfg::kWarps - 1) / Cfg::kWarps, nsm);
+    sweep_bricks_kernel<NC><<<grid, Cfg::kWarps * 32, smem, st>>>(a);
     MCEIK_LAUNCH_CHECK();
 }
 
-void BrickPlan::build(int nx_, int ny_, int nz_, int zc_, cudaStream_t st) {
-    if (nx_ == nx && ny_ == ny && nz_ == nz && zc_ == zc && nbricks > 0) return;
-    nx = nx_; ny = ny_; nz = nz_; zc = zc_;
+void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st) {
+    if (a.nfields_active == 0) return;
+    if (a.zc < 1 || a.zc > kMaxZc) throw CudaError("brick length out of range");
+    if (a.by == 16) launch_bricks_impl<4>(a, st);
+    else if (a.by == 8) launch_bricks_impl<2>(a, st);
+    else throw CudaError("brick width must be 8 or 16");
+}
+
+void BrickPlan::build(int nx_, int ny_, int nz_, int by_, int zc_, cudaStream_t st) {
+    if (nx_ == nx && ny_ == ny && nz_ == nz && zc_ == zc && by_ == by && nbricks > 0) return;
+    nx = nx_; ny = ny_; nz = nz_; zc = zc_; by = by_;
     nbx = (nx + kBx - 1) / kBx;
-    nby = (ny + kBy - 1) / kBy;
+    nby = (ny + by - 1) / by;
     nbz = (nz + zc - 1) / zc;
     if (nbx > 1023 || nby > 1023 || nbz > 1023) throw CudaError("grid too large for the brick plan");
     nbricks = nbx * nby * nbz;
@@ -344,7 +419,7 @@ void BrickPlan::release() {
     brick_order.release();
     blevel_ptr.release();
     nbricks = 0;
-    nx = ny = nz = zc = 0;
+    nx = ny = nz = zc = by = 0;
 }
 
 }  // namespace fsm
