@@ -241,6 +241,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
+            a.debug = getenv("MCEIK_FSM_DEBUG") ? atoi(getenv("MCEIK_FSM_DEBUG")) : 0;
             a.stats = getenv("MCEIK_FSM_STATS") ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
             MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
@@ -412,6 +413,9 @@ int mceik_ctx_create(int device, void *stream, mceik_ctx **out) {
             return -3;
         }
         DeviceGuard dg(device);
+        // The sweep kernel reads isolated 32-byte sectors (x-halo columns); the default 64-byte L2 fetch
+        // granularity would double their DRAM traffic.
+        if (!getenv("MCEIK_L2_FETCH_DEFAULT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
         mceik_ctx *c = new mceik_ctx();
         c->device = device;
         if (stream) {
@@ -455,7 +459,7 @@ int mceik_ctx_synchronize(mceik_ctx *c) {
 int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
     if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS && algo != MCEIK_FSM_ALGO_BRICKS)) return -1;
     c->fsm_algo = algo;
-    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(64, atoi(e)));
+    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(128, atoi(e)));
     if (const char *e = getenv("MCEIK_FSM_BY")) c->brick_by = atoi(e) == 16 ? 16 : 8;
     return 0;
 }

@@ -88,6 +88,7 @@ struct BrickArgs {
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
     const int *bc_node;           // flat node index of each (unique) boundary-condition node
     unsigned long long *stats;    // optional [4] cycle counters (MCEIK_FSM_STATS=1), else nullptr
+    int debug;                    // bottleneck experiments only (MCEIK_FSM_DEBUG): 1 no solver, 2 no stores, 4 no loads
 };
 void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
 
