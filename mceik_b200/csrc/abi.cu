@@ -245,7 +245,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.stats = getenv("MCEIK_FSM_STATS") ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
             MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
-            fsm::launch_iteration_bricks(a, st);
+            if (nx % 8 == 0 && a.by == 8 && !getenv("MCEIK_FSM_NO16")) fsm::launch_iteration_bricks16(a, st);
+            else fsm::launch_iteration_bricks(a, st);
             MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
             ctx->last_sweep_launches += 1;
             fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);

@@ -91,6 +91,8 @@ struct BrickArgs {
     int debug;                    // bottleneck experiments only (MCEIK_FSM_DEBUG): 1 no solver, 2 no stores, 4 no loads
 };
 void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
+// 16-byte-pair variant (fsm_bricks16.cu): requires nx % 8 == 0 and by == 8
+void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st);
 
 // device self-test of sqrt_fast / local_solve_sl against __dsqrt_rn / local_solve; d_bad[2] counts mismatches
 void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st);

@@ -1,0 +1,361 @@
+// fsm_bricks16.cu -- the streaming brick sweep kernel for grids with nx % 8 == 0 (sm_100a).
+//
+// Same algorithm, ring and scheduling as sweep_bricks_kernel (fsm_bricks.cu -- read its header
+// first); what changes is how the ring is fed and drained:
+//
+//   * every global <-> shared transfer moves a PAIR of x-adjacent nodes (16 bytes): cp.async.cg
+//     (L2 only -- no L1 line is allocated, so the 200+ KB of shared memory the rings take do not
+//     starve the copies of L1) and 128-bit stores.  3 copies and 1 store per lane and step instead
+//     of 5 and 2.
+//   * a ring row keeps the brick's x order of MEMORY (column q = x - x_lo at index q + 2, halo pairs
+//     (-2,-1) and (8,9) at indices 0..1 and 10..11), whatever the sweep direction, so pairs land in
+//     order; the sweep direction only decides which of the two x-neighbours is "upwind" and which
+//     slot it lives in.  Rows (y) and planes (z) stay in sweep order.
+//
+// nx % 8 == 0 makes every brick full in x and every pair 16-byte aligned; other grids use
+// sweep_bricks_kernel.  Bricks at the grid's x faces fetch their clamped halo column (a copy of the
+// boundary column itself, fsm3d.f90:495-499) with an 8-byte cp.async.
+#include <algorithm>
+#include <type_traits>
+#include <vector>
+#include "fsm.cuh"
+#include "fsm_solve.cuh"
+
+namespace mceik {
+namespace fsm {
+
+namespace {
+
+constexpr int kBx = 8, kBy = 8, kNC = 2;
+constexpr int kPrefetch = 2;
+constexpr int kRing = 9 + kPrefetch;
+constexpr int kURow = 12;                          // row: [pad(-2) halo(-1) | 0..7 | halo(8) pad(9)]
+constexpr int kUCells = kURow * (kBy + 2);
+constexpr int kSlot = kUCells + kBx * kBy;         // 184 doubles, 16-byte aligned
+constexpr int kMaxZc = 128;
+constexpr int kWarps = 12;
+constexpr int kProgShift = 12;
+constexpr int kLead = kBy + 3;
+constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int xgroup(int i) { return (i + 4) >> 2; }
+
+}  // namespace
+
+__global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
+    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc]
+
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const size_t nxy = (size_t)nx * ny, N = nxy * nz;
+    const int nf = a.nfields_active;
+    const long long per_sweep = (long long)a.nbricks * nf;
+    const long long ntasks = 8 * per_sweep;
+    // compute map: lane -> sweep column li and rows j0, j0 + 1
+    const int li = lane >> 2, j0 = kNC * (lane & 3);
+    const int ig = xgroup(li);
+    const bool xm_prev = (li & 3) == 0, xp_next = (li & 3) == 3;
+    // transfer map: lane -> pair (memory columns 2p, 2p + 1) of row jt
+    const int tp = lane & 3, jt = lane >> 2;
+    const int publish = a.publish;
+
+    while (true) {
+        long long t = 0;
+        if (lane == 0) t = (long long)atomicAdd(a.queue, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntasks) break;
+        const long long t_start = a.stats ? clock64() : 0;
+
+        // ---- ticket -> (sweep, brick level, brick, field)
+        const int s = (int)(t / per_sweep);
+        long long r = t - (long long)s * per_sweep;
+        int lo = 0, hi = a.nblevels;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)nf * __ldg(a.blevel_ptr + mid) <= r) lo = mid; else hi = mid;
+        }
+        r -= (long long)nf * __ldg(a.blevel_ptr + lo);
+        const int bidx = (int)(r / nf);
+        const int f = __ldg(a.active + (int)(r - (long long)bidx * nf));
+        const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + lo) + bidx);
+        const bool revx = (s & 1) != 0, revy = (s & 2) != 0, revz = (s & 4) != 0;  // fsm3d.f90:46-53
+        int I = packed & 1023, J = (packed >> 10) & 1023, K = packed >> 20;
+        if (revx) I = a.nbx - 1 - I;
+        if (revy) J = a.nby - 1 - J;
+        if (revz) K = a.nbz - 1 - K;
+        const int brick = (K * a.nby + J) * a.nbx + I;
+        int *done_f = a.done + (size_t)f * a.nbricks;
+
+        // ---- dependencies (see sweep_bricks_kernel)
+        const int *up_ptr = nullptr;
+        if (lane < 7) {
+            int di = 0, dj = 0, dk = 0;
+            if (lane == 1) di = -1; else if (lane == 2) di = 1;
+            else if (lane == 3) dj = -1; else if (lane == 4) dj = 1;
+            else if (lane == 5) dk = -1; else if (lane == 6) dk = 1;
+            const int NI = I + di, NJ = J + dj, NK = K + dk;
+            if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby && NK >= 0 && NK < a.nbz) {
+                int need = s << kProgShift;
+                if (dk != 0 && dk == (revz ? 1 : -1)) need = (s + 1) << kProgShift;
+                const int *p = done_f + ((NK * a.nby + NJ) * a.nbx + NI);
+                while (ld_acquire_gpu(p) < need) __nanosleep(400);
+            }
+        }
+        if (lane < 2) {
+            const int NI = I + (lane == 0 ? (revx ? 1 : -1) : 0), NJ = J + (lane == 1 ? (revy ? 1 : -1) : 0);
+            if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby) up_ptr = done_f + ((K * a.nby + NJ) * a.nbx + NI);
+        }
+        long long t_upwind = 0;
+        auto wait_upwind = [&](int steps_needed) {
+            const long long t0 = a.stats ? clock64() : 0;
+            if (up_ptr) {
+                const int need = (s << kProgShift) + steps_needed;
+                while (ld_acquire_gpu(up_ptr) < need) __nanosleep(200);
+            }
+            __syncwarp();
+            if (a.stats) t_upwind += clock64() - t0;
+        };
+        const long long t_deps = a.stats ? clock64() : 0;
+        wait_upwind(4 + kPrefetch + kLead);
+        __syncwarp();
+
+        // brick frame: x in memory order (q = x - x_lo), y and z in sweep order
+        const int x_lo = I * kBx, y_lo = J * kBy, z_lo = K * a.zc;
+        const int y_hi = min(y_lo + kBy, ny) - 1, z_hi = min(z_lo + a.zc, nz) - 1;
+        const int ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
+        const int yb = revy ? y_hi : y_lo, zb = revz ? z_hi : z_lo;
+        const int sx = revx ? -1 : 1, sy = revy ? -1 : 1, sz = revz ? -1 : 1;
+        double *uf = a.u + (size_t)f * N;
+        const double *sl = a.slow + (size_t)__ldg(a.field_model + f) * N;
+
+        // ---- boundary-condition nodes inside the brick (bit = j * 8 + i in sweep coordinates)
+        bool hasbc = false;
+        {
+            const int b0 = __ldg(a.bc_ptr + f), b1 = __ldg(a.bc_ptr + f + 1);
+            bool mine = false;
+            for (int n = b0 + lane; n < b1; n += 32) {
+                const int node = __ldg(a.bc_node + n);
+                const int gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
+                mine |= gx >= x_lo && gx < x_lo + kBx && gy >= y_lo && gy <= y_hi && gz >= z_lo && gz <= z_hi;
+            }
+            hasbc = __any_sync(0xffffffffu, mine);
+            if (hasbc) {
+                for (int k = lane; k < kMaxZc; k += 32) bcm[k] = 0ULL;
+                __syncwarp();
+                for (int n = b0 + lane; n < b1; n += 32) {
+                    const int node = __ldg(a.bc_node + n);
+                    const int gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
+                    if (gx >= x_lo && gx < x_lo + kBx && gy >= y_lo && gy <= y_hi && gz >= z_lo && gz <= z_hi) {
+                        const int i = revx ? x_lo + kBx - 1 - gx : gx - x_lo, j = (gy - yb) * sy, k = (gz - zb) * sz;
+                        atomicOr(bcm + k, 1ULL << (j * kBx + i));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- transfer descriptors of this lane (all per task): interior pair, slowness pair, halo pair
+        const long long zstride = (long long)sz * (long long)nxy;
+        const int klo = (zb - sz < 0 || zb - sz > nz - 1) ? 0 : -1;
+        const int khi = (zb + sz * ez < 0 || zb + sz * ez > nz - 1) ? ez - 1 : ez;
+        // interior pair (2tp, 2tp+1) of row jt: sweep index of its first node decides the x-group
+        const int gi = xgroup(revx ? kBx - 1 - 2 * tp : 2 * tp);
+        const int kofs_t = gi + jt + 2;
+        const size_t rowt = (size_t)zb * nxy + (size_t)min(max(yb + sy * jt, 0), ny - 1) * nx + x_lo + 2 * tp;
+        double *pu_t = uf + rowt;
+        const double *pf_t = sl + rowt;
+        const int cu_t = (jt + 1) * kURow + 2 * tp + 2, cf_t = kUCells + jt * kBx + 2 * tp;
+        const bool act_t = jt < ey;
+        // halo pair of lanes 0..23: 0-7 left x pair (q = -2,-1) of row h; 8-15 right x pair (q = 8,9) of row
+        // h-8; 16-19 row j = -1, pair h-16; 20-23 row j = By, pair h-20.  hmode: 0 none, 1 pair copy,
+        // 2 clamped single column (brick on the grid's x face: the halo repeats the boundary column)
+        int hmode = 0, kofs_h = 0, cu_h = 0;
+        const double *pu_h = uf;
+        if (lane < 16) {
+            const bool left = lane < 8;
+            const int hj = lane & 7;
+            const int ih = left ? (revx ? kBx : -1) : (revx ? -1 : kBx);  // sweep index of the needed halo column
+            kofs_h = xgroup(ih) + hj + 2;
+            const size_t row = (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx;
+            const bool inside = left ? x_lo >= 2 : x_lo + kBx + 1 <= nx - 1;
+            if (hj < ey) {
+                if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); pu_h = uf + row + (left ? x_lo - 2 : x_lo + kBx); }
+                else { hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10); pu_h = uf + row + (left ? x_lo : x_lo + kBx - 1); }
+            }
+        } else if (lane < 24) {
+            const bool low = lane < 20;
+            const int hp = lane & 3;
+            const int gh = xgroup(revx ? kBx - 1 - 2 * hp : 2 * hp);
+            const int hj = low ? -1 : kBy;
+            kofs_h = gh + hj + 2;
+            hmode = 1;
+            cu_h = (hj + 1) * kURow + 2 * hp + 2;
+            pu_h = uf + (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx + x_lo + 2 * hp;
+        }
+
+        int ld_slot = 0, ld_m = 0;
+        auto issue_slot = [&](auto steady_tag) {
+            constexpr bool kSteady = decltype(steady_tag)::value;
+            double *sp = U + ld_slot;
+            const int k = ld_m - kofs_t;
+            if (kSteady) {
+                const long long z = (long long)k * zstride;
+                cp_async16(sp + cu_t, pu_t + z);
+                cp_async16(sp + cf_t, pf_t + z);
+            } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
+                const long long z = (long long)min(max(k, klo), khi) * zstride;
+                cp_async16(sp + cu_t, pu_t + z);
+                if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + z);
+            }
+            const int kh = ld_m - kofs_h;
+            if (hmode == 1) {
+                if (kSteady || (kh >= 0 && kh < ez)) cp_async16(sp + cu_h, pu_h + (long long)kh * zstride);
+            } else if (hmode == 2) {
+                if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * zstride);
+            }
+            cp_async_commit();
+            ++ld_m;
+            ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
+        };
+        for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot(std::false_type());
+
+        // ---- compute descriptors
+        const int qx = revx ? kBx - 1 - li : li;            // memory column of this lane's sweep column
+        const int cu0 = (j0 + 1) * kURow + qx + 2;          // ring cell of compute column c: cu0 + c * kURow
+        const int cf0 = kUCells + j0 * kBx + qx;
+        bool act[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) act[c] = j0 + c < ey;
+        const int mc = ig - li + 2;
+        int oc = ((mc % kRing) + kRing) % kRing * kSlot;
+        int om = (oc == 0) ? (kRing - 1) * kSlot : oc - kSlot;
+        int op = (oc + kSlot == kRing * kSlot) ? 0 : oc + kSlot;
+        int st_slot = ((-3 % kRing) + kRing) % kRing * kSlot;
+
+        cp_async_wait<kPrefetch - 1>();
+        __syncwarp();
+        double self[kNC], zm[kNC];
+#pragma unroll
+        for (int c = 0; c < kNC; ++c) {
+            const int k = -li - j0 - c;
+            self[c] = 0.0; zm[c] = 0.0;
+            if (k == 0) {
+                self[c] = U[(ig + j0 + c + 2) * kSlot + cu0 + c * kURow];
+                zm[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
+            } else if (k == -1) {
+                self[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
+            }
+        }
+
+        const int nsteps = ez + kBy + 6;
+        auto step = [&](int l, auto steady_tag) {
+            constexpr bool kSteady = decltype(steady_tag)::value;
+            if ((l & (publish - 1)) == 0) wait_upwind(l + publish + 4 + kPrefetch + kLead);
+            issue_slot(steady_tag);
+            cp_async_wait<kPrefetch>();
+            __syncwarp();
+
+            const int k0 = l - li - j0;
+            bool go[kNC];
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) go[c] = kSteady || (act[c] && (unsigned)(k0 - c) < (unsigned)ez);
+            if (!kSteady && hasbc) {
+#pragma unroll
+                for (int c = 0; c < kNC; ++c)
+                    if (go[c] && ((bcm[k0 - c] >> ((j0 + c) * kBx + li)) & 1ULL)) go[c] = false;
+            }
+            const double *pm = U + om + cu0, *pc = U + oc + cu0, *pp = U + op + cu0;
+            const double *pxm = (xm_prev ? pm : pc) - sx, *pxp = (xp_next ? pp : pc) + sx;
+            double ux[kNC], uy[kNC], uz[kNC], fh[kNC], zp[kNC], nv[kNC];
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) {
+                zp[c] = pp[c * kURow];
+                ux[c] = dmin2(pxm[c * kURow], pxp[c * kURow]);
+                uy[c] = dmin2(pm[(c - 1) * kURow], pp[(c + 1) * kURow]);
+                uz[c] = dmin2(zm[c], zp[c]);
+                fh[c] = __dmul_rn(U[oc + cf0 + c * kBx], a.h);
+            }
+            local_solve_xn<kNC>(ux, uy, uz, fh, nv);
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) {
+                const bool upd = go[c] && nv[c] < self[c];  // u = MIN(u, ubar) (fsm3d.f90:477)
+                if (upd) U[oc + cu0 + c * kURow] = nv[c];
+                zm[c] = upd ? nv[c] : self[c];
+                self[c] = zp[c];
+            }
+            __syncwarp();
+
+            // slot l - 3 is final: write its pair of this lane back (one 16-byte store)
+            {
+                const int ks = l - 3 - kofs_t;
+                if (kSteady || (act_t && (unsigned)ks < (unsigned)ez)) {
+                    const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + cu_t);
+                    __stcg(reinterpret_cast<double2 *>(pu_t + (long long)ks * zstride), v);
+                }
+            }
+            om = oc; oc = op;
+            op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
+            st_slot = (st_slot + kSlot == kRing * kSlot) ? 0 : st_slot + kSlot;
+            if (((l + 1) & (publish - 1)) == 0 && l + 1 < nsteps) {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(done_f + brick, (s << kProgShift) + l + 1);
+                }
+            }
+        };
+        // steady window: all transfers, updates and stores of the step touch in-brick nodes of a full
+        // brick that is not on the grid's x faces and holds no boundary-condition node
+        const bool full = ey == kBy && !hasbc && x_lo >= 2 && x_lo + kBx + 1 <= nx - 1;
+        const int s_lo = full ? kBy + 6 : nsteps, s_hi = full ? ez - 3 - kPrefetch : nsteps;
+        int l = 0;
+        for (; l < min(s_lo, nsteps); ++l) step(l, std::false_type());
+        for (; l < s_hi; ++l) step(l, std::true_type());
+        for (; l < nsteps; ++l) step(l, std::false_type());
+
+        cp_async_wait<0>();
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            st_release_gpu(done_f + brick, (s + 1) << kProgShift);
+        }
+        __syncwarp();
+        if (a.stats && lane == 0) {
+            const long long t_end = clock64();
+            atomicAdd(a.stats + 0, (unsigned long long)(t_deps - t_start));
+            atomicAdd(a.stats + 1, (unsigned long long)t_upwind);
+            atomicAdd(a.stats + 2, (unsigned long long)(t_end - t_deps));
+            atomicAdd(a.stats + 3, 1ULL);
+        }
+    }
+}
+
+void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
+    if (a.nfields_active == 0) return;
+    if (a.zc < 1 || a.zc > kMaxZc || a.by != kBy || a.nx % kBx != 0) throw CudaError("bricks16: unsupported geometry");
+    const size_t smem = kWarpSmem * kWarps;
+    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, nsm = 0;
+    MCEIK_CUDA(cudaGetDevice(&dev));
+    MCEIK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const long long ntasks = 8LL * a.nbricks * a.nfields_active;
+    const int grid = (int)std::min<long long>((ntasks + kWarps - 1) / kWarps, nsm);
+    sweep_bricks16_kernel<<<grid, kWarps * 32, smem, st>>>(a);
+    MCEIK_LAUNCH_CHECK();
+}
+
+}  // namespace fsm
+}  // namespace mceik
