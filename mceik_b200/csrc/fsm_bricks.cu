@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(BrickCfg<NC>::kWarps * 32, 1) sweep_bricks_ker
 #pragma unroll
                 for (int c = 0; c < NC; ++c) nv[c] = __dadd_rn(dmin2(ux[c], dmin2(uy[c], uz[c])), fh[c]);
             } else {
-                local_solve_xn<NC>(ux, uy, uz, fh, nv);
+                local_solve_xn<NC>(ux, uy, uz, fh, go, nv);
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -382,10 +382,10 @@ __global__ void __launch_bounds__(BrickCfg<NC>::kWarps * 32, 1) sweep_bricks_ker
         // touch in-brick nodes only for l in [By + 6, ez - 3 - prefetch)
         const bool full = ex == kBx && ey == kBy && !hasbc;
         const int s_lo = full ? kBy + 6 : nsteps, s_hi = full ? ez - 3 - kPrefetch : nsteps;
-        int l = 0;
-        for (; l < min(s_lo, nsteps); ++l) step(l, std::false_type());
-        for (; l < s_hi; ++l) step(l, std::true_type());
-        for (; l < nsteps; ++l) step(l, std::false_type());
+        for (int l = 0; l < nsteps; ++l) {
+            if (l >= s_lo && l < s_hi) step(l, std::true_type());
+            else step(l, std::false_type());
+        }
         cp_async_wait<0>();
         __syncwarp();
         if (lane == 0) {

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 uz[c] = dmin2(zm[c], zp[c]);
                 fh[c] = __dmul_rn(U[oc + cf0 + c * kBx], a.h);
             }
-            local_solve_xn<kNC>(ux, uy, uz, fh, nv);
+            local_solve_xn<kNC>(ux, uy, uz, fh, go, nv);
 #pragma unroll
             for (int c = 0; c < kNC; ++c) {
                 const bool upd = go[c] && nv[c] < self[c];  // u = MIN(u, ubar) (fsm3d.f90:477)
@@ -321,10 +321,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         // brick that is not on the grid's x faces and holds no boundary-condition node
         const bool full = ey == kBy && !hasbc && x_lo >= 2 && x_lo + kBx + 1 <= nx - 1;
         const int s_lo = full ? kBy + 6 : nsteps, s_hi = full ? ez - 3 - kPrefetch : nsteps;
-        int l = 0;
-        for (; l < min(s_lo, nsteps); ++l) step(l, std::false_type());
-        for (; l < s_hi; ++l) step(l, std::true_type());
-        for (; l < nsteps; ++l) step(l, std::false_type());
+        for (int l = 0; l < nsteps; ++l) {
+            if (l >= s_lo && l < s_hi) step(l, std::true_type());
+            else step(l, std::false_type());
+        }
 
         cp_async_wait<0>();
         __syncwarp();
