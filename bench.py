@@ -86,11 +86,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/roofline.json), or None."""
+def ncu_traffic(kernel, units_per_launch):
+    """DRAM bytes per launch of `kernel`: bytes per unit of work (node-update / event) from the committed
+    ncu --set full capture (profiles/roofline.json) x the units one launch of THIS run processes; or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline.json")) as f:
-            return json.load(f)[kernel]["dram_bytes_per_launch"]
+            return json.load(f)[kernel]["dram_bytes_per_unit"] * units_per_launch
     except Exception:
         return None
 
@@ -292,8 +293,8 @@ def run_ours(a):
     peak, peak_src = measured_peak()
     sweep_updates = updates  # every node-update of the solve happens inside the sweep kernel
     ach = BYTES_PER_UPDATE * sweep_updates / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "sweep_bricks_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if ach else None, "traffic": ncu_traffic("sweep_bricks_kernel"),
+    roofline = {"bound": "hbm", "kernel": "sweep_bricks16_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak if ach else None, "traffic": ncu_traffic("sweep_bricks16_kernel", sweep_updates / max(sweep_launches, 1)),
                 "peak_source": peak_src, "launches": sweep_launches,
                 "avg_launch_ms": sweep_ms / max(sweep_launches, 1),
                 "algorithmic_bytes_per_launch": BYTES_PER_UPDATE * sweep_updates / max(sweep_launches, 1),
@@ -416,7 +417,7 @@ def run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, d_u, d_
     peak, peak_src = measured_peak()
     ach = alg_bytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "locate_uniform_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic("locate_uniform_kernel"), "peak_source": peak_src,
+            "traffic": ncu_traffic("locate_uniform_kernel", ne), "peak_source": peak_src,
             "fp64_tflops": 8.0 * nuse * N * steps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
             "note": "tables are reused across the 8 events of a CTA, so the binding limit is the fp64 pipe "
                     "(8 non-fused flops per event x pick x node), not HBM; frac may exceed 1"}

@@ -21,7 +21,7 @@ for r in rows:
     d[1] += float(r[-1]) / 1e6
 total_ms = sum(v[1] for v in tot.values())
 with open(os.path.join(P, f"launches_{tag}.md"), "w") as f:
-    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --skip-cpu`, N=1\n\n")
+    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 64`, N=1\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised launches: "
             "compare SHARES, not absolute times; the first 400 launches of the command).\n\n")
     f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
@@ -40,10 +40,13 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 roof = {}
+plain = json.load(open(os.path.join(G, "bench_plain.json")))
+units_per_launch = {"sweep_bricks16_kernel": plain["config"]["fields_per_gpu"] * plain["config"]["grid"][0] ** 3 * 8,
+                    "locate_uniform_kernel": int(plain["events"]["config"]["workload"].split(": ")[1].split(" events")[0])}
 out = open(os.path.join(P, f"ncu_summary_{tag}.md"), "w")
 out.write(f"# ncu --set full summaries ({tag})\n\nCaptured with `tools/profile_round.sh` (clock control none, one launch each, "
           "from the bench command).  Numbers under ncu are never bench values.\n")
-for rep, kern in (("prof_fsm.ncu-rep", "sweep_bricks_kernel"), ("prof_gs.ncu-rep", "locate_uniform_kernel")):
+for rep, kern in (("prof_fsm.ncu-rep", "sweep_bricks16_kernel"), ("prof_gs.ncu-rep", "locate_uniform_kernel")):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
         continue
@@ -61,7 +64,10 @@ for rep, kern in (("prof_fsm.ncu-rep", "sweep_bricks_kernel"), ("prof_gs.ncu-rep
     roof[kern] = {"dram_bytes_per_launch": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
                   "dram_bytes_read": tobytes("dram__bytes_read.sum"), "dram_bytes_write": tobytes("dram__bytes_write.sum"),
                   "duration_ms_under_ncu": float(m["gpu__time_duration.sum"][1]) * (1.0 if m["gpu__time_duration.sum"][0] == "ms" else 1e-3),
-                  "source": f"profiles/ncu_summary_{tag}.md ({rep})"}
+                  "units_per_launch": units_per_launch[kern],
+                  "unit": "node-updates" if kern.startswith("sweep") else "events",
+                  "source": f"profiles/ncu_summary_{tag}.md ({rep}); command: python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 64"}
+    roof[kern]["dram_bytes_per_unit"] = roof[kern]["dram_bytes_per_launch"] / units_per_launch[kern]
     lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), path, "", "14"],
                            capture_output=True, text=True).stdout
     out.write("\nStall reasons and hottest source lines (warp-state sampling):\n\n```\n" + lines[lines.index("--- total samples"):] + "```\n")
