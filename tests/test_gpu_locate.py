@@ -226,3 +226,42 @@ def test_catalog_struct_entry(gpu_ctx):
     assert np.array_equal(iopt, cat["true_node"])
     assert np.allclose(hypo[:, 3], cat["tori"], atol=1e-5)
     assert np.array_equal(hypo[:, 0], X[iopt].astype(np.float64))
+
+
+def test_large_catalog_noise_free_round_trip(gpu_ctx):
+    """Size-independent property at a large size (128^3 grid, 64 device-generated tables, 512 events, 10 %
+    masked picks): picks synthesised from the tables at a node are located on exactly that node with
+    t0 = origin time; sharding the events into two halves gives the same answers (no data-path collective)."""
+    import ctypes as C
+    import torch
+    from mceik_b200 import _lib
+    from mceik_b200.locate import Locator
+    from mceik_b200 import sharding
+    n, h, ns = 128, 1000.0, 32
+    N, ntab, ne = n ** 3, 64, 512
+    rng = np.random.default_rng(5)
+    X, Y, Z = np.repeat(rng.uniform(0, (n - 1) * h, ns), 2), np.repeat(rng.uniform(0, (n - 1) * h, ns), 2), np.full(ntab, (n - 1) * h)
+    V = np.tile(np.array([5000.0, 5000.0 / np.sqrt(3.0)]), ns)
+    d_tab = torch.empty((ntab, N), dtype=torch.float32, device="cuda")
+    p = lambda x: x.ctypes.data_as(_lib.c_dbl_p)
+    assert _lib.load().mceik_homogeneous_tables_dev(gpu_ctx.handle, n, n, n, 0.0, 0.0, 0.0, h, h, h, ntab, p(X), p(Y), p(Z), p(V),
+                                                    C.c_void_p(d_tab.data_ptr()), N) == 0
+    true_node = rng.integers(0, N, ne)
+    tori = rng.uniform(0, 10, ne)
+    tobs = (d_tab[:, torch.from_numpy(true_node).cuda()].T.double().cpu().numpy() + tori[:, None]).ravel()
+    use = rng.uniform(size=ne * ntab) >= 0.1
+    tid = np.where(use, np.tile(np.arange(ntab), ne), -1).astype(np.int32)
+    var = rng.choice(np.array([0.1, 0.25, 0.5]), ne * ntab)
+    obs_ptr = (np.arange(ne + 1) * ntab).astype(np.int32)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_device(d_tab, N)
+    iopt, t0, obj = loc.locate_host(2, obs_ptr, tid, tobs, var)
+    assert np.array_equal(iopt, true_node)
+    assert np.allclose(t0, tori, rtol=0, atol=1e-5) and np.all(obj < 1e-9)
+    parts = []
+    for r in range(2):
+        lo, hi, lptr, p0, p1 = sharding.shard_events(obs_ptr, 2, r)
+        parts.append(loc.locate_host(2, lptr, tid[p0:p1], tobs[p0:p1], var[p0:p1]))
+    assert np.array_equal(np.concatenate([q[0] for q in parts]), iopt)
+    assert np.array_equal(np.concatenate([q[1] for q in parts]), t0)
+    assert np.array_equal(np.concatenate([q[2] for q in parts]), obj)
