@@ -50,7 +50,7 @@ struct mceik_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     fsm::TilePlan plan;
     fsm::BrickPlan bplan;
-    int brick_zc = 64, brick_by = 8;
+    int brick_zc = 256, brick_by = 8;
     // eikonal workspaces
     DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
     // locator state
@@ -460,7 +460,7 @@ int mceik_ctx_synchronize(mceik_ctx *c) {
 int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
     if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS && algo != MCEIK_FSM_ALGO_BRICKS)) return -1;
     c->fsm_algo = algo;
-    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(128, atoi(e)));
+    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(256, atoi(e)));
     if (const char *e = getenv("MCEIK_FSM_BY")) c->brick_by = atoi(e) == 16 ? 16 : 8;
     return 0;
 }

@@ -31,7 +31,7 @@ constexpr int kBx = 8;                   // brick cross-section: kBx x (4 * NC) 
 constexpr int kPrefetch = 2;             // ring slots loaded ahead of their first reader
 constexpr int kRing = 9 + kPrefetch;     // ring depth in slots (see "ring" below)
 constexpr int kURow = kBx + 2;           // cell row stride inside a slot (doubles), halo included
-constexpr int kMaxZc = 128;              // longest brick (mask storage)
+constexpr int kMaxZc = 256;              // longest brick (mask storage)
 // Progress word of a (field, brick): (sweeps completed << kProgShift) while idle, and
 // (sweep << kProgShift) + steps completed while the brick is being swept.
 constexpr int kProgShift = 12;
@@ -45,7 +45,7 @@ template <int NC> struct BrickCfg {
     static constexpr int kSlot = kUCells + kBx * kBy;   // one slot: travel-time cells (with halo) + slowness cells
     static constexpr int kHalo = 2 * kBy + 2 * kBx;     // halo cells per slot
     static constexpr int kMaskWords = (kBx * kBy + 63) / 64;
-    static constexpr int kWarps = NC == 2 ? 12 : 8;  // 12 x 15.4 KB ring = 185 KB; the rest of the 228 KB stays L1 for cp.async.ca
+    static constexpr int kWarps = NC == 2 ? 12 : 7;  // NC = 2: 12 x 16.5 KB = 198 KB; the rest of the 228 KB stays L1 for cp.async.ca
     static constexpr int kLead = kBy + 3;
     static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc * kMaskWords;
 };

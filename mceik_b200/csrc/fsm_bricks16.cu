@@ -32,7 +32,7 @@ constexpr int kRing = 9 + kPrefetch;
 constexpr int kURow = 12;                          // row: [pad(-2) halo(-1) | 0..7 | halo(8) pad(9)]
 constexpr int kUCells = kURow * (kBy + 2);
 constexpr int kSlot = kUCells + kBx * kBy;         // 184 doubles, 16-byte aligned
-constexpr int kMaxZc = 128;
+constexpr int kMaxZc = 256;
 constexpr int kWarps = 12;
 constexpr int kProgShift = 12;
 constexpr int kLead = kBy + 3;
