@@ -212,6 +212,13 @@ int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *o
 int mceik_locate_batched_dev(mceik_ctx *ctx, int job, int nevents, int nobs_total, int max_picks, const int *d_obs_ptr,
                              const int *d_table_id, const double *d_tobs_cor, const double *d_varobs,
                              const double *d_tori, int *d_iopt, double *d_t0opt, double *d_objopt);
+/* Full posterior volume of ONE event against the resident tables: the
+ * per-event logPDF the reference accumulates, logPDF[g] = -sum_i (w_i/sqrt2 * (tobs_i - (T_i[g] + t0[g])))^2
+ * (locate.f90:436-463, fp32 tables promoted to fp64), optionally its fp32 copy (what the location file
+ * stores, h5io.c:714-819) and the origin-time grid t0[g].  Picks as in mceik_locate_batched_host
+ * (table_id < 0 = unused); job 1 uses t0 = tori everywhere.  Host output arrays [ngrd]; any may be NULL. */
+int mceik_locate_event_logpdf_host(mceik_ctx *ctx, int job, int npicks, const int *table_id, const double *tobs_cor,
+                                   const double *varobs, double tori, double *logpdf, float *logpdf4, double *t0grid);
 /* Catalogue form (mceik_struct.h layouts): picks are catalog->obsPtr CSR, table from
  * (statPtr, pickType), static correction from stations->pcorr/scorr; hypo[4*nevents] needs
  * mceik_locate_set_grid().  iopt/obj may be NULL. */

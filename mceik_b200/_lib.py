@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmceik_b200.so")
+LIB_PATH = os.environ.get("MCEIK_B200_LIB") or os.path.join(_HERE, "lib", "libmceik_b200.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -85,6 +85,8 @@ SIGNATURES = {
     "mceik_locate_batched_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p,
                                             c_int_p, c_dbl_p, c_dbl_p]),
     "mceik_locate_batched_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8),
+    "mceik_locate_event_logpdf_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_dbl_p, c_dbl_p, C.c_double,
+                                                 c_dbl_p, c_flt_p, c_dbl_p]),
     "mceik_locate_catalog": (C.c_int, [C.c_void_p, C.POINTER(CatalogStruct), C.POINTER(StationsStruct), C.c_int,
                                        c_dbl_p, c_int_p, c_dbl_p]),
 }

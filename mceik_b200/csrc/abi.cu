@@ -300,6 +300,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             float ms = 0.f;
             MCEIK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
             ctx->last_sweep_ms += ms;
+            if (getenv("MCEIK_FSM_TRACE")) printf("[fsm trace] iter %d: %zu active fields, sweep kernel %.2f ms\n", k, active.size(), ms);
         }
         std::vector<int> still;
         for (int f : active) {
@@ -647,6 +648,44 @@ int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *o
         MCEIK_CUDA(cudaMemcpyAsync(iopt, out, sizeof(int) * nevents, cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaMemcpyAsync(t0opt, out + q_t0, sizeof(double) * nevents, cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaMemcpyAsync(objopt, out + q_obj, sizeof(double) * nevents, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+int mceik_locate_event_logpdf_host(mceik_ctx *ctx, int job, int npicks, const int *table_id, const double *tobs_cor,
+                                   const double *varobs, double tori, double *logpdf, float *logpdf4, double *t0grid) {
+    return guarded([&]() -> int {
+        if (!ctx || !ctx->d_tables) { set_error("mceik_locate_event_logpdf_host: no travel-time tables set"); return -1; }
+        if (job != 1 && job != 2) { set_error("mceik_locate_event_logpdf_host: job %d not supported", job); return 1; }
+        if (npicks < 1 || !table_id || !tobs_cor || !varobs) { set_error("mceik_locate_event_logpdf_host: bad argument"); return -1; }
+        for (int p = 0; p < npicks; ++p)
+            if (table_id[p] >= ctx->ntables) { set_error("mceik_locate_event_logpdf_host: table id out of range"); return -1; }
+        DeviceGuard dg(ctx->device);
+        cudaStream_t st = ctx->stream;
+        const size_t ng = (size_t)ctx->ngrd;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+        const size_t o_ptr = take(sizeof(int) * 2), o_tid = take(sizeof(int) * npicks), o_tobs = take(sizeof(double) * npicks);
+        const size_t o_var = take(sizeof(double) * npicks), o_w0 = take(sizeof(double) * npicks), o_w1 = take(sizeof(double) * npicks);
+        const size_t o_nuse = take(sizeof(int)), o_pdf = take(sizeof(double) * ng), o_pdf4 = take(sizeof(float) * ng), o_t0 = take(sizeof(double) * ng);
+        char *b = static_cast<char *>(ctx->ws_gs_misc.ensure(off));
+        const int ptr[2] = {0, npicks};
+        MCEIK_CUDA(cudaMemcpyAsync(b + o_ptr, ptr, sizeof(ptr), cudaMemcpyHostToDevice, st));
+        MCEIK_CUDA(cudaMemcpyAsync(b + o_tid, table_id, sizeof(int) * npicks, cudaMemcpyHostToDevice, st));
+        MCEIK_CUDA(cudaMemcpyAsync(b + o_tobs, tobs_cor, sizeof(double) * npicks, cudaMemcpyHostToDevice, st));
+        MCEIK_CUDA(cudaMemcpyAsync(b + o_var, varobs, sizeof(double) * npicks, cudaMemcpyHostToDevice, st));
+        gs::launch_prepare(1, reinterpret_cast<int *>(b + o_ptr), reinterpret_cast<int *>(b + o_tid),
+                           reinterpret_cast<double *>(b + o_var), reinterpret_cast<double *>(b + o_w0),
+                           reinterpret_cast<double *>(b + o_w1), reinterpret_cast<int *>(b + o_nuse), st);
+        gs::launch_event_grid(ctx->ngrd, ctx->ldgrd, npicks, reinterpret_cast<int *>(b + o_tid), reinterpret_cast<double *>(b + o_tobs),
+                              reinterpret_cast<double *>(b + o_w0), reinterpret_cast<double *>(b + o_w1), job == 2, tori,
+                              ctx->d_tables, logpdf ? reinterpret_cast<double *>(b + o_pdf) : nullptr,
+                              logpdf4 ? reinterpret_cast<float *>(b + o_pdf4) : nullptr,
+                              t0grid ? reinterpret_cast<double *>(b + o_t0) : nullptr, st);
+        if (logpdf) MCEIK_CUDA(cudaMemcpyAsync(logpdf, b + o_pdf, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
+        if (logpdf4) MCEIK_CUDA(cudaMemcpyAsync(logpdf4, b + o_pdf4, sizeof(float) * ng, cudaMemcpyDeviceToHost, st));
+        if (t0grid) MCEIK_CUDA(cudaMemcpyAsync(t0grid, b + o_t0, sizeof(double) * ng, cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaStreamSynchronize(st));
         return 0;
     });

@@ -261,9 +261,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         }
 
         const int nsteps = ez + kBy + 6;
-        auto step = [&](int l, auto steady_tag) {
+        auto step_core = [&](int l, auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
-            if ((l & (publish - 1)) == 0) wait_upwind(l + publish + 4 + kPrefetch + kLead);
             issue_slot(steady_tag);
             cp_async_wait<kPrefetch>();
             __syncwarp();
@@ -309,29 +308,38 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             om = oc; oc = op;
             op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
             st_slot = (st_slot + kSlot == kRing * kSlot) ? 0 : st_slot + kSlot;
-            if (((l + 1) & (publish - 1)) == 0 && l + 1 < nsteps) {
+        };
+        // progress of the brick is published (and the upwind bricks' progress awaited) every `publish` steps
+        auto wait_chunk = [&](int l) { wait_upwind(l + publish + 4 + kPrefetch + kLead); };
+        auto publish_chunk = [&](int l1) {
+            if (l1 < nsteps) {
                 __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    st_release_gpu(done_f + brick, (s << kProgShift) + l + 1);
-                }
+                if (lane == 0) st_release_gpu(done_f + brick, (s << kProgShift) + l1);
             }
         };
+        auto step = [&](int l) {
+            if ((l & (publish - 1)) == 0) wait_chunk(l);
+            step_core(l, std::false_type());
+            if (((l + 1) & (publish - 1)) == 0) publish_chunk(l + 1);
+        };
         // steady window: all transfers, updates and stores of the step touch in-brick nodes of a full
-        // brick that is not on the grid's x faces and holds no boundary-condition node
+        // brick that is not on the grid's x faces and holds no boundary-condition node; it runs in whole
+        // publication chunks with no per-step bookkeeping
         const bool full = ey == kBy && !hasbc && x_lo >= 2 && x_lo + kBx + 1 <= nx - 1;
-        const int s_lo = full ? kBy + 6 : nsteps, s_hi = full ? ez - 3 - kPrefetch : nsteps;
-        for (int l = 0; l < nsteps; ++l) {
-            if (l >= s_lo && l < s_hi) step(l, std::true_type());
-            else step(l, std::false_type());
+        int s_lo = (kBy + 6 + publish - 1) & ~(publish - 1), s_hi = (ez - 3 - kPrefetch) & ~(publish - 1);
+        if (!full || s_hi <= s_lo) s_lo = s_hi = nsteps;
+        int l = 0;
+        for (; l < s_lo; ++l) step(l);
+        for (; l < s_hi; l += publish) {
+            wait_chunk(l);
+            for (int q = 0; q < publish; ++q) step_core(l + q, std::true_type());
+            publish_chunk(l + publish);
         }
+        for (; l < nsteps; ++l) step(l);
 
         cp_async_wait<0>();
         __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            st_release_gpu(done_f + brick, (s + 1) << kProgShift);
-        }
+        if (lane == 0) st_release_gpu(done_f + brick, (s + 1) << kProgShift);
         __syncwarp();
         if (a.stats && lane == 0) {
             const long long t_end = clock64();

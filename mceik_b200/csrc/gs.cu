@@ -531,6 +531,43 @@ template void launch_full_grid<float>(int, size_t, int, const int *, const float
                                       float, const float *, float *, float *, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
+// Per-event posterior volume from the resident fp32 tables (the logPDF the reference accumulates
+// per event, locate.f90:436-463: logPDF = -sum res^2, fp32 tables promoted to fp64), plus the
+// origin-time grid; fp32 copy = what the location file stores (h5io.c:714-819).
+// ------------------------------------------------------------------------------------------
+__global__ void event_grid_kernel(int ngrd, size_t ldgrd, int npicks, const int *__restrict__ table_id,
+                                  const double *__restrict__ tobs, const double *__restrict__ w_t0,
+                                  const double *__restrict__ w_obj, int want_ot, double t0use,
+                                  const float *__restrict__ tables, double *__restrict__ logpdf,
+                                  float *__restrict__ logpdf4, double *__restrict__ t0out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngrd) return;
+    double t0 = want_ot ? 0.0 : t0use;
+    if (want_ot)
+        for (int j = 0; j < npicks; ++j)
+            if (table_id[j] >= 0)
+                t0 = __dadd_rn(t0, __dmul_rn(w_t0[j], __dsub_rn(tobs[j], (double)__ldg(tables + (size_t)table_id[j] * ldgrd + g))));
+    double obj = 0.0;
+    for (int j = 0; j < npicks; ++j)
+        if (table_id[j] >= 0) {
+            const double res = __dmul_rn(w_obj[j], __dsub_rn(tobs[j], __dadd_rn((double)__ldg(tables + (size_t)table_id[j] * ldgrd + g), t0)));
+            obj = __dadd_rn(obj, __dmul_rn(res, res));
+        }
+    if (logpdf) logpdf[g] = -obj;
+    if (logpdf4) logpdf4[g] = __double2float_rn(-obj);
+    if (t0out) t0out[g] = t0;
+}
+
+void launch_event_grid(int ngrd, size_t ldgrd, int npicks, const int *d_table_id, const double *d_tobs, const double *d_w_t0,
+                       const double *d_w_obj, int want_ot, double t0use, const float *d_tables, double *d_logpdf,
+                       float *d_logpdf4, double *d_t0, cudaStream_t st) {
+    if (ngrd == 0) return;
+    event_grid_kernel<<<(ngrd + 255) / 256, 256, 0, st>>>(ngrd, ldgrd, npicks, d_table_id, d_tobs, d_w_t0, d_w_obj, want_ot,
+                                                          t0use, d_tables, d_logpdf, d_logpdf4, d_t0);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // locate_minLoc{Double64,Float64} (locate.c:811-851)
 // ------------------------------------------------------------------------------------------
 constexpr int kMinlocBlocks = 148 * 4;

@@ -59,6 +59,10 @@ template <typename T>
 void launch_full_grid(int ngrd, size_t ldgrd, int nuse, const int *d_row, const T *d_tobs, const T *d_w_t0,
                       const T *d_w_obj, int want_ot, T t0use, const T *d_test, T *d_t0, T *d_obj,
                       cudaStream_t st);
+// one event, resident fp32 tables: logPDF = -objective (fp64 and/or fp32) and the origin-time grid
+void launch_event_grid(int ngrd, size_t ldgrd, int npicks, const int *d_table_id, const double *d_tobs, const double *d_w_t0,
+                       const double *d_w_obj, int want_ot, double t0use, const float *d_tables, double *d_logpdf,
+                       float *d_logpdf4, double *d_t0, cudaStream_t st);
 // first index of the strict minimum (locate.c:811-851); result written to d_out[0]
 template <typename T>
 void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st);

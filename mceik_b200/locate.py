@@ -157,6 +157,22 @@ class Locator:
             raise _lib.MceikError(f"mceik_locate_batched_host rc={rc}: {_lib.last_error()}")
         return iopt[:ne], t0[:ne], obj[:ne]
 
+    def event_logpdf(self, job, table_id, tobs_cor, varobs, tori=0.0, want_t0=True, want_f32=False):
+        """Posterior volume of one event: (logPDF fp64 [ngrd], logPDF fp32 or None, t0 grid or None);
+        logPDF = -objective (locate.f90:458-461)."""
+        table_id = np.ascontiguousarray(table_id, dtype=np.int32)
+        tobs_cor = np.ascontiguousarray(tobs_cor, dtype=np.float64)
+        varobs = np.ascontiguousarray(varobs, dtype=np.float64)
+        pdf = np.empty(self.ngrd, dtype=np.float64)
+        pdf4 = np.empty(self.ngrd, dtype=np.float32) if want_f32 else None
+        t0 = np.empty(self.ngrd, dtype=np.float64) if want_t0 else None
+        rc = self.lib.mceik_locate_event_logpdf_host(self.ctx.handle, int(job), table_id.size, _ptr(table_id, c_int_p),
+                                                     _ptr(tobs_cor, c_dbl_p), _ptr(varobs, c_dbl_p), float(tori),
+                                                     _ptr(pdf, c_dbl_p), _ptr(pdf4, c_flt_p), _ptr(t0, c_dbl_p))
+        if rc != 0:
+            raise _lib.MceikError(f"mceik_locate_event_logpdf_host rc={rc}: {_lib.last_error()}")
+        return pdf, pdf4, t0
+
     def locate_device(self, job, nevents, max_picks, d_obs_ptr, d_table_id, d_tobs_cor, d_varobs, d_tori, d_iopt,
                       d_t0opt, d_objopt):
         """All arguments are CUDA torch tensors (int32 / float64); asynchronous on the context stream."""

@@ -298,6 +298,36 @@ done:
     return rc;
 }
 
+/* Per-event posterior volume of the catalogue flavour: logPDF[g] = -objective[g] (locate.f90:458-461)
+ * and t0[g], one event, picks given as (table id < 0 = unused, corrected pick time, variance).      */
+int oracle_event_logpdf(int job, int ngrd, size_t ldgrd, const float *tables, int npicks, const int *table_id,
+                        const double *tobs_cor, const double *varobs, double tori, double *logpdf, double *t0)
+{
+    if (job != 1 && job != 2) return 1;
+    double xnorm = 0.0;
+    for (int i = 0; i < npicks; i++)
+        if (table_id[i] >= 0) xnorm = xnorm + 1.0 / varobs[i];
+    for (int g = 0; g < ngrd; g++) { logpdf[g] = 0.0; t0[g] = job == 2 ? 0.0 : tori; }
+    if (job == 2)
+        for (int i = 0; i < npicks; i++) {
+            if (table_id[i] < 0) continue;
+            const float *tt = tables + ldgrd * (size_t)table_id[i];
+            double w = (1.0 / varobs[i]) / xnorm, to = tobs_cor[i];
+            for (int g = 0; g < ngrd; g++) t0[g] = t0[g] + w * (to - (double)tt[g]);
+        }
+    for (int i = 0; i < npicks; i++) {
+        if (table_id[i] < 0) continue;
+        const float *tt = tables + ldgrd * (size_t)table_id[i];
+        double w = (1.0 / varobs[i]) * SQRT2I_D, to = tobs_cor[i];
+        for (int g = 0; g < ngrd; g++) {
+            double res = w * (to - ((double)tt[g] + t0[g]));
+            logpdf[g] = logpdf[g] + res * res;
+        }
+    }
+    for (int g = 0; g < ngrd; g++) logpdf[g] = -logpdf[g];
+    return 0;
+}
+
 /* ---- analytic homogeneous tables: homog.c:594-621 -------------------------------------
  * t[iz*nx*ny+iy*nx+ix] = sqrt((xs-x)^2+(ys-y)^2+(zs-z)^2) * (1/vel), x = x0 + ix*dx     */
 int oracle_homogeneous_traveltimes(int nx, int ny, int nz, double x0, double y0, double z0,

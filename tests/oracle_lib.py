@@ -173,3 +173,18 @@ def locate3d_catalog(job, ngrd, ldgrd, tables, nobs, nevents, luseObs, statPtr, 
                                    _p(a[8], c_flt_p), _p(a[9], c_flt_p), _p(hypo, c_dbl_p), _p(iopt, c_int_p),
                                    _p(objmin, c_dbl_p))
     return rc, hypo, iopt, objmin
+
+
+def event_logpdf(job, ngrd, ldgrd, tables, table_id, tobs_cor, varobs, tori=0.0):
+    """Per-event posterior volume (catalogue flavour) -> (rc, logPDF, t0 grid)."""
+    L = lib()
+    L.oracle_event_logpdf.restype = C.c_int
+    tables = np.ascontiguousarray(tables, dtype=np.float32)
+    tid = np.ascontiguousarray(table_id, dtype=np.int32)
+    tc = np.ascontiguousarray(tobs_cor, dtype=np.float64)
+    var = np.ascontiguousarray(varobs, dtype=np.float64)
+    pdf, t0 = np.empty(ngrd), np.empty(ngrd)
+    rc = L.oracle_event_logpdf(C.c_int(job), C.c_int(ngrd), C.c_size_t(ldgrd), _p(tables, c_flt_p), C.c_int(tid.size),
+                               _p(tid, c_int_p), _p(tc, c_dbl_p), _p(var, c_dbl_p), C.c_double(tori), _p(pdf, c_dbl_p),
+                               _p(t0, c_dbl_p))
+    return rc, pdf, t0

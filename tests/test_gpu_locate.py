@@ -265,3 +265,26 @@ def test_large_catalog_noise_free_round_trip(gpu_ctx):
     assert np.array_equal(np.concatenate([q[0] for q in parts]), iopt)
     assert np.array_equal(np.concatenate([q[1] for q in parts]), t0)
     assert np.array_equal(np.concatenate([q[2] for q in parts]), obj)
+
+
+def test_event_posterior_volume(gpu_ctx):
+    """Full logPDF / t0 volumes of one event equal the oracle bit for bit; the fp32 copy
+    is the rounded fp64 volume; its argmax is the event located by the batched search."""
+    from mceik_b200.locate import Locator
+    n, h, tables, cat = _c1_case(nevents=3, n=30, nstat=6)
+    ngrd = n ** 3
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    nobs = cat["nobs"]
+    for e in range(3):
+        sl = slice(e * nobs, (e + 1) * nobs)
+        tid = np.where(cat["luseObs"][sl] == 1, np.arange(nobs), -1).astype(np.int32)
+        tid[e] = -1
+        tc = cat["tobs"][sl] + np.random.default_rng(e).normal(0, 0.01, nobs)
+        for job in (2, 1):
+            pdf, pdf4, t0 = loc.event_logpdf(job, tid, tc, cat["varobs"][sl], tori=cat["tori"][e], want_f32=True)
+            rc, pdf_ref, t0_ref = O.event_logpdf(job, ngrd, ngrd, tables, tid, tc, cat["varobs"][sl], cat["tori"][e])
+            assert rc == 0 and np.array_equal(pdf, pdf_ref) and np.array_equal(t0, t0_ref)
+            assert np.array_equal(pdf4, pdf_ref.astype(np.float32))
+            iopt, t0o, objo = loc.locate_host(job, np.array([0, nobs], np.int32), tid, tc, cat["varobs"][sl], cat["tori"][e:e + 1])
+            assert iopt[0] == int(np.argmax(pdf)) and objo[0] == -pdf[iopt[0]] and t0o[0] == t0[iopt[0]]
