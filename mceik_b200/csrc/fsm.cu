@@ -438,10 +438,21 @@ __global__ void convergence_kernel(size_t n, const int *__restrict__ active_fiel
     double *u0f = u0 + (size_t)f * n;
     unsigned int bad = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double v = uf[i];
-        if (!(fabs(__dsub_rn(u0f[i], v)) < tol)) ++bad;
-        u0f[i] = v;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double v[4], o[4];  // four independent streams per thread keep enough bytes in flight
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const size_t i = i0 + q * stride;
+            if (i < n) { v[q] = __ldcs(uf + i); o[q] = __ldcs(u0f + i); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const size_t i = i0 + q * stride;
+            if (i < n) {
+                if (!(fabs(__dsub_rn(o[q], v[q])) < tol)) ++bad;
+                __stcs(u0f + i, v[q]);
+            }
+        }
     }
     for (int off = 16; off > 0; off >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, off);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonconv + f, (unsigned long long)bad);
@@ -450,7 +461,7 @@ __global__ void convergence_kernel(size_t n, const int *__restrict__ active_fiel
 void launch_convergence(size_t n, int nfields, const int *d_active_fields, double tol, const double *d_u,
                         double *d_u0, unsigned long long *d_nonconv, cudaStream_t st) {
     if (nfields == 0) return;
-    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 148 * 4), nfields);
+    dim3 grid((unsigned)std::min<size_t>((n + 1023) / 1024, 148 * 4), nfields);
     convergence_kernel<<<grid, 256, 0, st>>>(n, d_active_fields, tol, d_u, d_u0, d_nonconv);
     MCEIK_LAUNCH_CHECK();
 }

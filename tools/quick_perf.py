@@ -48,7 +48,7 @@ if not a.skip_fsm:
         torch.cuda.synchronize()
         dt = time.time() - t
         upd = sol.node_updates
-        print(f"FSM {n}^3 x {a.fields} fields: iters={list(iters)} {dt*1e3:.1f} ms  {upd/dt/1e9:.2f} Gupd/s  "
+        print(f"FSM {n}^3 x {a.fields} fields: iters={int(min(iters))}..{int(max(iters))} (mean {float(np.mean(iters)):.2f}) {dt*1e3:.1f} ms  {upd/dt/1e9:.2f} Gupd/s  "
               f"{24*upd/dt/1e9:.0f} GB/s algorithmic  sweep-kernel {sol.sweep_stats[0]:.1f} ms in {sol.sweep_stats[1]} launches", flush=True)
     del d_u
 
