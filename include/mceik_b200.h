@@ -219,6 +219,13 @@ int mceik_locate_batched_dev(mceik_ctx *ctx, int job, int nevents, int nobs_tota
  * (table_id < 0 = unused); job 1 uses t0 = tori everywhere.  Host output arrays [ngrd]; any may be NULL. */
 int mceik_locate_event_logpdf_host(mceik_ctx *ctx, int job, int npicks, const int *table_id, const double *tobs_cor,
                                    const double *varobs, double tori, double *logpdf, float *logpdf4, double *t0grid);
+/* LOCATE_OPTNODE (locate.f90:75-117) on one device: 0-based first index of the maximum of pdf[ngrd] (MAXLOC). */
+int mceik_locate_optnode_host(mceik_ctx *ctx, int ngrd, const double *pdf, int *node);
+/* LOCATE_NORMALIZE_PDF (locate.f90:43-64): pdf *= 1/sum(pdf) in place; *sum (may be NULL) receives the sum.
+ * Returns 1 and leaves pdf untouched when the sum is exactly zero.  The sum uses a fixed reduction tree
+ * (bit-reproducible run to run); its order differs from the Fortran SUM, so it agrees with a sequential
+ * sum to ~1e-13 relative, not bit for bit (tests use 1e-12). */
+int mceik_locate_normalize_pdf_host(mceik_ctx *ctx, int ngrd, double *pdf, double *sum);
 /* Catalogue form (mceik_struct.h layouts): picks are catalog->obsPtr CSR, table from
  * (statPtr, pickType), static correction from stations->pcorr/scorr; hypo[4*nevents] needs
  * mceik_locate_set_grid().  iopt/obj may be NULL. */

@@ -87,6 +87,8 @@ SIGNATURES = {
     "mceik_locate_batched_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8),
     "mceik_locate_event_logpdf_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_dbl_p, c_dbl_p, C.c_double,
                                                  c_dbl_p, c_flt_p, c_dbl_p]),
+    "mceik_locate_optnode_host": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, c_int_p]),
+    "mceik_locate_normalize_pdf_host": (C.c_int, [C.c_void_p, C.c_int, c_dbl_p, c_dbl_p]),
     "mceik_locate_catalog": (C.c_int, [C.c_void_p, C.POINTER(CatalogStruct), C.POINTER(StationsStruct), C.c_int,
                                        c_dbl_p, c_int_p, c_dbl_p]),
 }

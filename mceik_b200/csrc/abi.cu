@@ -691,6 +691,48 @@ int mceik_locate_event_logpdf_host(mceik_ctx *ctx, int job, int npicks, const in
     });
 }
 
+int mceik_locate_optnode_host(mceik_ctx *ctx, int ngrd, const double *pdf, int *node) {
+    return guarded([&]() -> int {
+        if (!ctx || ngrd < 1 || !pdf || !node) { set_error("mceik_locate_optnode_host: bad argument"); return -1; }
+        DeviceGuard dg(ctx->device);
+        cudaStream_t st = ctx->stream;
+        const size_t o_s = align_up(sizeof(double) * (size_t)ngrd), o_out = o_s + align_up(gs::minloc_scratch_bytes());
+        char *b = static_cast<char *>(ctx->ws_gs_misc.ensure(o_out + 256));
+        MCEIK_CUDA(cudaMemcpyAsync(b, pdf, sizeof(double) * (size_t)ngrd, cudaMemcpyHostToDevice, st));
+        gs::launch_minloc<double>(ngrd, reinterpret_cast<double *>(b), reinterpret_cast<int *>(b + o_out), b + o_s,
+                                  gs::minloc_scratch_bytes(), st, /*maxloc=*/true);
+        MCEIK_CUDA(cudaMemcpyAsync(node, b + o_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
+int mceik_locate_normalize_pdf_host(mceik_ctx *ctx, int ngrd, double *pdf, double *sum) {
+    return guarded([&]() -> int {
+        if (!ctx || ngrd < 1 || !pdf) { set_error("mceik_locate_normalize_pdf_host: bad argument"); return -1; }
+        DeviceGuard dg(ctx->device);
+        cudaStream_t st = ctx->stream;
+        const size_t o_s = align_up(sizeof(double) * (size_t)ngrd), o_out = o_s + align_up(gs::minloc_scratch_bytes());
+        char *b = static_cast<char *>(ctx->ws_gs_misc.ensure(o_out + 256));
+        double xsum = 0.0;
+        MCEIK_CUDA(cudaMemcpyAsync(b, pdf, sizeof(double) * (size_t)ngrd, cudaMemcpyHostToDevice, st));
+        gs::launch_sum(ngrd, reinterpret_cast<double *>(b), reinterpret_cast<double *>(b + o_out), b + o_s,
+                       gs::minloc_scratch_bytes(), st);
+        MCEIK_CUDA(cudaMemcpyAsync(&xsum, b + o_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        if (sum) *sum = xsum;
+        if (xsum == 0.0) {  // locate.f90:56-60
+            printf(" locate_optloc: Division by zero\n");
+            set_error("mceik_locate_normalize_pdf_host: the PDF sums to zero");
+            return 1;
+        }
+        gs::launch_scale(ngrd, 1.0 / xsum, reinterpret_cast<double *>(b), st);  // xsumi = one/xsum; DSCAL (locate.f90:61-62)
+        MCEIK_CUDA(cudaMemcpyAsync(pdf, b, sizeof(double) * (size_t)ngrd, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+}
+
 static void fill_hypo(const mceik_ctx *ctx, int nevents, const int *iopt, const double *t0, double *hypo) {
     for (int e = 0; e < nevents; ++e) {
         const int i = iopt[e];

@@ -575,11 +575,11 @@ struct MinPart { double v; int i; int pad; };
 size_t minloc_scratch_bytes() { return sizeof(MinPart) * kMinlocBlocks; }
 
 template <typename T>
-__global__ void minloc_stage1(int n, const T *__restrict__ x, MinPart *__restrict__ parts) {
+__global__ void minloc_stage1(int n, const T *__restrict__ x, MinPart *__restrict__ parts, double sign) {
     double bv = d_inf();
     int bi = INT_MAX;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double v = (double)x[i];  // float -> double is exact and order preserving
+        const double v = sign * (double)x[i];  // float -> double and the sign flip (MAXLOC) are exact, order preserving
         if (better(v, i, bv, bi)) { bv = v; bi = i; }
     }
     __shared__ double sv[8];
@@ -614,17 +614,56 @@ __global__ void minloc_stage2(int nparts, const MinPart *__restrict__ parts, con
 }
 
 template <typename T>
-void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st, bool maxloc) {
     if (scratch_bytes < minloc_scratch_bytes()) throw CudaError("minloc scratch too small");
     MinPart *parts = reinterpret_cast<MinPart *>(d_scratch);
     const int blocks = std::max(1, std::min(kMinlocBlocks, (n + 255) / 256));
-    minloc_stage1<T><<<blocks, 256, 0, st>>>(n, d_x, parts);
+    minloc_stage1<T><<<blocks, 256, 0, st>>>(n, d_x, parts, maxloc ? -1.0 : 1.0);
     MCEIK_LAUNCH_CHECK();
     minloc_stage2<T><<<1, 32, 0, st>>>(blocks, parts, d_x, d_out);
     MCEIK_LAUNCH_CHECK();
 }
-template void launch_minloc<double>(int, const double *, int *, void *, size_t, cudaStream_t);
-template void launch_minloc<float>(int, const float *, int *, void *, size_t, cudaStream_t);
+template void launch_minloc<double>(int, const double *, int *, void *, size_t, cudaStream_t, bool);
+template void launch_minloc<float>(int, const float *, int *, void *, size_t, cudaStream_t, bool);
+
+// ------------------------------------------------------------------------------------------
+// LOCATE_NORMALIZE_PDF (locate.f90:43-64): sum of the grid (fixed reduction tree -> the same bits
+// on every run; the order differs from the Fortran SUM, see the tolerance in the header) and DSCAL.
+// ------------------------------------------------------------------------------------------
+__global__ void sum_stage1(int n, const double *__restrict__ x, double *__restrict__ parts) {
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += x[i];
+    __shared__ double sv[8];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc += sv[w];
+        parts[blockIdx.x] = acc;
+    }
+}
+__global__ void sum_stage2(int nparts, const double *__restrict__ parts, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += 32) acc += parts[p];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+__global__ void scale_kernel(int n, double factor, double *__restrict__ x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = __dmul_rn(x[i], factor);
+}
+void launch_sum(int n, const double *d_x, double *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (scratch_bytes < sizeof(double) * kMinlocBlocks) throw CudaError("sum scratch too small");
+    const int blocks = std::max(1, std::min(kMinlocBlocks, (n + 255) / 256));
+    sum_stage1<<<blocks, 256, 0, st>>>(n, d_x, reinterpret_cast<double *>(d_scratch));
+    MCEIK_LAUNCH_CHECK();
+    sum_stage2<<<1, 32, 0, st>>>(blocks, reinterpret_cast<const double *>(d_scratch), d_out);
+    MCEIK_LAUNCH_CHECK();
+}
+void launch_scale(int n, double factor, double *d_x, cudaStream_t st) {
+    if (n == 0) return;
+    scale_kernel<<<std::min(kMinlocBlocks, (n + 255) / 256), 256, 0, st>>>(n, factor, d_x);
+    MCEIK_LAUNCH_CHECK();
+}
 
 }  // namespace gs
 }  // namespace mceik

@@ -65,7 +65,11 @@ void launch_event_grid(int ngrd, size_t ldgrd, int npicks, const int *d_table_id
                        float *d_logpdf4, double *d_t0, cudaStream_t st);
 // first index of the strict minimum (locate.c:811-851); result written to d_out[0]
 template <typename T>
-void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st,
+                   bool maxloc = false);
+// deterministic grid sum (scratch: minloc_scratch_bytes()) and in-place scaling (LOCATE_NORMALIZE_PDF, locate.f90:43-64)
+void launch_sum(int n, const double *d_x, double *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+void launch_scale(int n, double factor, double *d_x, cudaStream_t st);
 size_t minloc_scratch_bytes();
 
 }  // namespace gs

@@ -173,6 +173,24 @@ class Locator:
             raise _lib.MceikError(f"mceik_locate_event_logpdf_host rc={rc}: {_lib.last_error()}")
         return pdf, pdf4, t0
 
+    def optnode(self, pdf):
+        """LOCATE_OPTNODE (locate.f90:75-117): 0-based first index of the maximum."""
+        pdf = np.ascontiguousarray(pdf, dtype=np.float64)
+        node = C.c_int(0)
+        rc = self.lib.mceik_locate_optnode_host(self.ctx.handle, pdf.size, _ptr(pdf, c_dbl_p), C.byref(node))
+        if rc != 0:
+            raise _lib.MceikError(f"mceik_locate_optnode_host rc={rc}: {_lib.last_error()}")
+        return node.value
+
+    def normalize_pdf(self, pdf):
+        """LOCATE_NORMALIZE_PDF (locate.f90:43-64): in place pdf /= sum(pdf); returns (ierr, sum)."""
+        assert pdf.dtype == np.float64 and pdf.flags.c_contiguous
+        xsum = C.c_double(0.0)
+        rc = self.lib.mceik_locate_normalize_pdf_host(self.ctx.handle, pdf.size, _ptr(pdf, c_dbl_p), C.byref(xsum))
+        if rc not in (0, 1):
+            raise _lib.MceikError(f"mceik_locate_normalize_pdf_host rc={rc}: {_lib.last_error()}")
+        return rc, xsum.value
+
     def locate_device(self, job, nevents, max_picks, d_obs_ptr, d_table_id, d_tobs_cor, d_varobs, d_tori, d_iopt,
                       d_t0opt, d_objopt):
         """All arguments are CUDA torch tensors (int32 / float64); asynchronous on the context stream."""

@@ -288,3 +288,25 @@ def test_event_posterior_volume(gpu_ctx):
             assert np.array_equal(pdf4, pdf_ref.astype(np.float32))
             iopt, t0o, objo = loc.locate_host(job, np.array([0, nobs], np.int32), tid, tc, cat["varobs"][sl], cat["tori"][e:e + 1])
             assert iopt[0] == int(np.argmax(pdf)) and objo[0] == -pdf[iopt[0]] and t0o[0] == t0[iopt[0]]
+
+
+def test_pdf_helpers(gpu_ctx):
+    """LOCATE_OPTNODE = first index of the maximum (bit-exact); LOCATE_NORMALIZE_PDF = pdf * (1/sum) with the
+    sum within 1e-12 relative of the sequential Fortran-order sum (locate.f90:43-117); zero sum -> ierr 1."""
+    from mceik_b200.locate import Locator
+    loc = Locator(gpu_ctx)
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 1000, 300_001):
+        pdf = np.exp(-rng.uniform(0.0, 30.0, n))
+        if n > 10:
+            pdf[[n // 3, n // 2]] = pdf.max() * 2.0   # tie: the first one wins
+        assert loc.optnode(pdf) == int(np.argmax(pdf))
+        seq = float(np.cumsum(pdf)[-1])               # sequential sum, the order of the reference's SUM at -O2
+        work = pdf.copy()
+        ierr, xsum = loc.normalize_pdf(work)
+        assert ierr == 0 and abs(xsum - seq) <= 1e-12 * abs(seq)
+        assert np.array_equal(work, pdf * (1.0 / xsum))   # DSCAL by the reciprocal (locate.f90:61-62)
+        assert abs(work.sum() - 1.0) < 1e-12
+    zero = np.zeros(64)
+    ierr, xsum = loc.normalize_pdf(zero)
+    assert ierr == 1 and xsum == 0.0 and not zero.any()
