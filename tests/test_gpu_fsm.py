@@ -37,7 +37,9 @@ def test_xfsm3d_case_matches_oracle(gpu_ctx, algo):
     assert sol.node_updates == nx * ny * nz * 8 * it
 
 
-@pytest.mark.parametrize("shape", [(37, 50, 21), (16, 16, 16), (5, 70, 3), (33, 17, 48)])
+@pytest.mark.parametrize("shape", [(37, 50, 21), (16, 16, 16), (5, 70, 3), (33, 17, 48),
+                                   # more than one brick layer in z (bricks span 256 planes), incl. a 1-plane layer
+                                   (16, 24, 300), (8, 8, 257), (12, 9, 260)])
 def test_random_model_two_sources_bit_exact(gpu_ctx, shape):
     """Heterogeneous random slowness, partial tiles, two sources seeding one field."""
     from mceik_b200.eikonal import EikonalSolver
@@ -112,6 +114,25 @@ def test_maxit_cap_and_edge_sources(gpu_ctx, algo):
         assert np.array_equal(u[f], ref)
     _, ierr, _ = O.eikonal_serial(nx, ny, nz, h, slow, 0.0, xs[1], ys[1], zs[1])
     assert ierr == 1
+
+
+def test_argument_errors_and_empty_batch(gpu_ctx):
+    """Bad sizes are refused before anything is allocated; an empty batch is a no-op."""
+    from mceik_b200 import _lib
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 16, 8, 8, 10.0
+    slow = np.full((1, nx * ny * nz), 1e-3)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h)
+    u, _, iters, ferr = sol.solve_host(slow, np.zeros(0, np.int32), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0))
+    assert u.shape[0] == 0 and iters.size == 0 and sol.node_updates == 0
+    with pytest.raises(_lib.MceikError, match="field_model"):
+        sol.solve_host(slow, [1], [0.0], [55.0], [33.0], [41.0])
+    big = EikonalSolver(gpu_ctx, 2048, 2048, 512, h)   # 2^31 nodes: refused, nothing is dereferenced
+    import ctypes as C
+    one_i, one_d = (C.c_int * 2)(0, 1), (C.c_double * 1)(55.0)
+    rc = big.lib.mceik_fsm_solve_batched_dev(gpu_ctx.handle, C.byref(big.grid), 1, C.c_void_p(256), 1, one_i, one_i, one_d,
+                                             one_d, one_d, one_d, None, None, 0, one_i, one_i)
+    assert rc != 0 and "2^31" in _lib.last_error()
 
 
 def test_serial_driver_lifecycle(gpu_ctx):
