@@ -149,7 +149,11 @@ def cpu_fsm_sample(a):
     n = a.grid
     slow = cases.checkerboard_slowness(n, n, n, cell=32)
     xs, ys, zs, _ = rank_fields(a, 0, 1)
-    cores = os.cpu_count() or 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = O.set_threads(avail)  # explicit: torchrun exports OMP_NUM_THREADS=1 to its children
     t = time.time()
     u, ierr, it = O.eikonal_serial(n, n, n, H, slow, 0.0, xs[0], ys[0], zs[0], tol=1e-6, maxit=20)
     dt = time.time() - t
@@ -336,7 +340,7 @@ def run_ours(a):
         events = run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, d_u, d_tab)
 
     cpu = None
-    if rank == 0 and not a.skip_cpu:
+    if rank == 0 and world == 1 and not a.skip_cpu:  # reported at N = 1 only (the contract); --impl reference covers N > 1
         v, cores, desc, _ = cpu_fsm_sample(a)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
@@ -432,7 +436,7 @@ def run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, d_u, d_
            "h2d_bytes_per_step": int(obs_ptr_h.nbytes + tid_h.nbytes + tobs_h.nbytes + var_h.nbytes),
            "d2h_bytes_per_step": int(ne * 20), "api": "mceik_locate_batched_host (tables resident in HBM)"}
     cpu = None
-    if rank == 0 and not a.skip_cpu:
+    if rank == 0 and world == 1 and not a.skip_cpu:
         # bounded CPU sample: first 32 tables only (2.1 GB on the host), events restricted to those picks
         sub = 32
         cores = os.cpu_count() or 1

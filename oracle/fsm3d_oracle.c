@@ -197,6 +197,19 @@ static void eval_update3d(int nx, int ny, int nz, int revx, int revy, int revz, 
     }
 }
 
+/* Thread count of the OpenMP region above (bench.py's CPU legs: torchrun exports OMP_NUM_THREADS=1).
+ * n <= 0 leaves the setting alone; returns the number of threads the next solve will use. */
+#ifdef _OPENMP
+#include <omp.h>
+int oracle_set_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int oracle_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* sweep table, fsm3d.f90:46-53: (revx,revy,revz) per sweep */
 static const int k_sweep[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {1, 1, 0},
                                   {0, 0, 1}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};

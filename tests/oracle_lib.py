@@ -188,3 +188,10 @@ def event_logpdf(job, ngrd, ldgrd, tables, table_id, tobs_cor, varobs, tori=0.0)
                                _p(tid, c_int_p), _p(tc, c_dbl_p), _p(var, c_dbl_p), C.c_double(tori), _p(pdf, c_dbl_p),
                                _p(t0, c_dbl_p))
     return rc, pdf, t0
+
+
+def set_threads(n=0):
+    """OpenMP threads of the FSM oracle (n <= 0: query only) -> threads the next solve uses."""
+    L = lib()
+    L.oracle_set_threads.restype = C.c_int
+    return int(L.oracle_set_threads(C.c_int(int(n))))
