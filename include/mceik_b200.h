@@ -20,6 +20,7 @@
 #ifndef MCEIK_B200_H
 #define MCEIK_B200_H 1
 
+#include <stdbool.h>
 #include <stddef.h>
 #include "mceik_b200_types.h"
 
@@ -72,6 +73,24 @@ int locate_l2_gridSearch__float64(const int ldgrd, const int ngrd, const int nob
                                   const float t0use, const int *mask, const float *tobs,
                                   const float *tcorr, const float *varobs, const float *test,
                                   float *t0, float *objfn);
+/* L1 flavour of the single-event search -- replaces locate_l1_gridSearch__double64 (locate.c:1205-1335; SURVEY.md
+ * section 8f row 3).  PARITY UNPINNED: the reference cannot link this function (its weighted median is declared at
+ * locate.c:73 and defined nowhere), so there is no reference behaviour to compare with; the arithmetic below is
+ * the reference's own, the median definition is ours, and the oracle restates both.
+ *   used picks: mask[i] == 0, catalogue order; w_i = 1/varobs[i]; when iwantOT == 1 and |sum w - 1| > 1e-14 the
+ *   weights are scaled by 1/sum w (locate.c:1263-1273; the reference's running sum indexes the packed array with
+ *   the unpacked index, :1245 -- with masked picks that is a defect and is not reproduced).
+ *   iwantOT == 1: t0[g] = weighted median of r_i = tobs[i] - test[i*ldgrd+g]; else t0[g] = t0use.
+ *   objfn[g] = sum_i w_i * |(tobs[i] - test[i*ldgrd+g]) - t0[g]|, accumulated in pick order (locate.c:1320-1321).
+ * Weighted median of (x_k, w_k): sort by (x, original index) ascending; W = sum of w in that order; the first k whose
+ * running sum exceeds W/2 gives x_k; a running sum exactly equal to W/2 gives (x_k + x_{k+1})/2 (the ordinary
+ * median for equal weights).  At most 128 used picks.  Returns 0, or 1 on bad arguments. */
+int locate_l1_gridSearch__double64(int ldgrd, int ngrd, int nobs, int iwantOT, double t0use, const int *mask,
+                                   const double *tobs, const double *varobs, const double *test, double *t0,
+                                   double *objfn);
+/* The weighted median above as a host function with the prototype the reference declares (locate.c:73-77): perm
+ * (may be NULL) is an ordering the caller keeps between calls, *lsort tells whether it had to be rebuilt. */
+double weightedMedian__double(int n, const double *x, const double *w, int *perm, bool *lsort, int *ierr);
 /* first index of the strict minimum (locate.c:811-851) */
 int locate_minLocDouble64(const int n, const double *x);
 int locate_minLocFloat64(const int n, const float *x);

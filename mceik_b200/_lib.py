@@ -52,6 +52,9 @@ SIGNATURES = {
     "eikonal3d_finalize": (None, [c_int_p, c_int_p]),
     "locate_l2_gridSearch__double64": (C.c_int, [C.c_int] * 4 + [C.c_double, c_int_p] + [c_dbl_p] * 6),
     "locate_l2_gridSearch__float64": (C.c_int, [C.c_int] * 4 + [C.c_float, c_int_p] + [c_flt_p] * 6),
+    "locate_l1_gridSearch__double64": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_int_p, c_dbl_p, c_dbl_p,
+                                                 c_dbl_p, c_dbl_p, c_dbl_p]),
+    "weightedMedian__double": (C.c_double, [C.c_int, c_dbl_p, c_dbl_p, c_int_p, C.POINTER(C.c_bool), c_int_p]),
     "locate_minLocDouble64": (C.c_int, [C.c_int, c_dbl_p]),
     "locate_minLocFloat64": (C.c_int, [C.c_int, c_flt_p]),
     "locate3d_gridsearch__double64": (None, [c_int_p] * 5 + [c_dbl_p] * 4 + [c_int_p]),

@@ -952,6 +952,105 @@ int l2_gridsearch_c(const char *fcnm, int ldgrd, int ngrd, int nobs, int iwantOT
     return 0;
 }
 
+// Host-side weighted median in the form locate.c:73 declares (the reference defines it nowhere):
+// perm is a candidate ordering kept by the caller between calls; *lsort tells whether it had to be redone.
+double weighted_median_host(int n, const double *x, const double *w, int *perm, bool *lsort, int *ierr) {
+    if (ierr) *ierr = 0;
+    if (lsort) *lsort = false;
+    if (n < 1 || !x || !w) {
+        if (ierr) *ierr = 1;
+        return 0.0;
+    }
+    std::vector<int> own;
+    if (!perm) {
+        own.resize(n);
+        for (int i = 0; i < n; ++i) own[i] = i;
+        perm = own.data();
+    }
+    bool ok = true;
+    std::vector<char> seen(n, 0);
+    for (int i = 0; i < n && ok; ++i) {
+        if (perm[i] < 0 || perm[i] >= n || seen[perm[i]]) ok = false;
+        else seen[perm[i]] = 1;
+    }
+    auto before = [&](int a, int b) { return x[a] < x[b] || (x[a] == x[b] && a < b); };
+    for (int i = 1; i < n && ok; ++i)
+        if (!before(perm[i - 1], perm[i])) ok = false;
+    if (!ok) {
+        for (int i = 0; i < n; ++i) perm[i] = i;
+        std::sort(perm, perm + n, before);
+        if (lsort) *lsort = true;
+    }
+    double W = 0.0;
+    for (int k = 0; k < n; ++k) W = W + w[perm[k]];
+    const double half = 0.5 * W;
+    double cum = 0.0;
+    for (int k = 0; k < n; ++k) {
+        cum = cum + w[perm[k]];
+        if (cum > half) return x[perm[k]];
+        if (cum == half) return k + 1 < n ? 0.5 * (x[perm[k]] + x[perm[k + 1]]) : x[perm[k]];
+    }
+    return x[perm[n - 1]];
+}
+
+int l1_gridsearch_c(int ldgrd, int ngrd, int nobs, int iwantOT, double t0use, const int *mask, const double *tobs,
+                    const double *varobs, const double *test, double *t0, double *objfn) {
+    const char *fcnm = "locate_l1_gridSearch__double64";
+    if (ldgrd < ngrd || ngrd < 0 || nobs < 1 || !mask || !tobs || !varobs || !test || !t0 || !objfn) {
+        printf("%s: Error invalid argument\n", fcnm);
+        return 1;
+    }
+    // locate.c:1236-1246 (weights of the unmasked picks, packed) and :1263-1273 (normalisation, analytic-t0 branch only)
+    std::vector<int> rows;
+    std::vector<double> tc, wt;
+    double wtsum = 0.0;
+    for (int i = 0; i < nobs; ++i) {
+        if (mask[i] != 0) continue;
+        wt.push_back(1.0 / varobs[i]);
+        tc.push_back(tobs[i]);
+        rows.push_back(i);
+        wtsum = wtsum + wt.back();
+    }
+    if (iwantOT == 1 && fabs(wtsum - 1.0) > 1.e-14) {
+        const double wtsumi = 1.0 / wtsum;
+        for (double &w : wt) w = w * wtsumi;
+    }
+    if (ngrd == 0) return 0;
+    if ((int)rows.size() > gs::kL1MaxObs) {
+        printf("%s: Error more than %d used observations\n", fcnm, gs::kL1MaxObs);
+        return 1;
+    }
+    mceik_ctx *c = default_ctx();
+    if (!c) return 1;
+    const int rc = guarded([&]() -> int {
+        DeviceGuard dg(c->device);
+        cudaStream_t st = c->stream;
+        const int nuse = (int)rows.size();
+        const size_t row_bytes = sizeof(double) * (size_t)ngrd, ld = (size_t)ldgrd;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+        const size_t o_test = take(sizeof(double) * ld * std::max(nuse, 1)), o_t0 = take(row_bytes), o_obj = take(row_bytes);
+        const size_t o_tobs = take(sizeof(double) * std::max(nuse, 1)), o_wt = take(sizeof(double) * std::max(nuse, 1));
+        char *b = static_cast<char *>(c->ws_gs_misc.ensure(off));
+        for (int j = 0; j < nuse; ++j)
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_test + sizeof(double) * ld * j, test + ld * (size_t)rows[j], row_bytes,
+                                       cudaMemcpyHostToDevice, st));
+        if (nuse) {
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_tobs, tc.data(), sizeof(double) * nuse, cudaMemcpyHostToDevice, st));
+            MCEIK_CUDA(cudaMemcpyAsync(b + o_wt, wt.data(), sizeof(double) * nuse, cudaMemcpyHostToDevice, st));
+        }
+        gs::launch_l1_grid(ngrd, ld, nuse, reinterpret_cast<double *>(b + o_tobs), reinterpret_cast<double *>(b + o_wt),
+                           iwantOT == 1, t0use, reinterpret_cast<double *>(b + o_test), reinterpret_cast<double *>(b + o_t0),
+                           reinterpret_cast<double *>(b + o_obj), st);
+        MCEIK_CUDA(cudaMemcpyAsync(t0, b + o_t0, row_bytes, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaMemcpyAsync(objfn, b + o_obj, row_bytes, cudaMemcpyDeviceToHost, st));
+        MCEIK_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    });
+    if (rc != 0) printf("%s: %s\n", fcnm, mceik_last_error());
+    return rc == 0 ? 0 : 1;
+}
+
 template <typename T>
 void gridsearch_f90(const char *fcnm, int ldgrd, int ngrd, int nobs, int iwantOT, const int *mask, const T *tobs,
                     const T *varobs, const T *test, T *logPDF, int *ierr, T eps) {
@@ -1017,6 +1116,14 @@ int locate_l2_gridSearch__float64(const int ldgrd, const int ngrd, const int nob
                                   const float *test, float *t0, float *objfn) {
     return l2_gridsearch_c<float>("locate_l2_gridSearch__float64", ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, tcorr,
                                   varobs, test, t0, objfn, 0.7071067811865475f);
+}
+int locate_l1_gridSearch__double64(const int ldgrd, const int ngrd, const int nobs, const int iwantOT, const double t0use,
+                                   const int *mask, const double *tobs, const double *varobs, const double *test,
+                                   double *t0, double *objfn) {
+    return l1_gridsearch_c(ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, varobs, test, t0, objfn);
+}
+double weightedMedian__double(const int n, const double *x, const double *w, int *perm, bool *lsort, int *ierr) {
+    return weighted_median_host(n, x, w, perm, lsort, ierr);
 }
 int locate_minLocDouble64(const int n, const double *x) { return minloc_host<double>(n, x); }
 int locate_minLocFloat64(const int n, const float *x) { return minloc_host<float>(n, x); }

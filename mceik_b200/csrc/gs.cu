@@ -568,6 +568,57 @@ void launch_event_grid(int ngrd, size_t ldgrd, int npicks, const int *d_table_id
 }
 
 // ------------------------------------------------------------------------------------------
+// L1 flavour, one event (locate_l1_gridSearch__double64, locate.c:1205-1335): origin time = weighted
+// median of the residuals tobs_i - T_i[g] (weights 1/var, normalised), misfit = sum w_i |res_i - t0|.
+// The reference declares its weighted median (locate.c:73) but defines it nowhere; the definition
+// used here is in include/mceik_b200.h.  One thread per grid node: stable insertion sort of the
+// (residual, weight) pairs in local memory, then one pass over the cumulative weights.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double weighted_median_sorted(int n, const double *x, const double *w) {
+    double W = 0.0;
+    for (int k = 0; k < n; ++k) W = __dadd_rn(W, w[k]);
+    const double half = __dmul_rn(0.5, W);
+    double cum = 0.0;
+    for (int k = 0; k < n; ++k) {
+        cum = __dadd_rn(cum, w[k]);
+        if (cum > half) return x[k];
+        if (cum == half) return k + 1 < n ? __dmul_rn(0.5, __dadd_rn(x[k], x[k + 1])) : x[k];
+    }
+    return n > 0 ? x[n - 1] : 0.0;
+}
+
+__global__ void l1_grid_kernel(int ngrd, size_t ldgrd, int nuse, const double *__restrict__ tobs,
+                               const double *__restrict__ wt, int want_ot, double t0use,
+                               const double *__restrict__ test, double *__restrict__ t0out, double *__restrict__ obj) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngrd) return;
+    double t0 = t0use;
+    if (want_ot) {
+        double x[kL1MaxObs], w[kL1MaxObs];
+        for (int i = 0; i < nuse; ++i) {  // picks arrive in catalogue order; equal residuals keep that order
+            const double r = __dsub_rn(tobs[i], test[(size_t)i * ldgrd + g]);
+            int k = i;
+            while (k > 0 && x[k - 1] > r) { x[k] = x[k - 1]; w[k] = w[k - 1]; --k; }
+            x[k] = r; w[k] = wt[i];
+        }
+        t0 = weighted_median_sorted(nuse, x, w);
+    }
+    double acc = 0.0;
+    for (int i = 0; i < nuse; ++i)  // locate.c:1320-1321
+        acc = __dadd_rn(acc, __dmul_rn(wt[i], fabs(__dsub_rn(__dsub_rn(tobs[i], test[(size_t)i * ldgrd + g]), t0))));
+    t0out[g] = t0;
+    obj[g] = acc;
+}
+
+void launch_l1_grid(int ngrd, size_t ldgrd, int nuse, const double *d_tobs, const double *d_wt, int want_ot, double t0use,
+                    const double *d_test, double *d_t0, double *d_obj, cudaStream_t st) {
+    if (ngrd == 0) return;
+    if (nuse > kL1MaxObs) throw CudaError("L1 grid search: more than kL1MaxObs used observations");
+    l1_grid_kernel<<<(ngrd + 127) / 128, 128, 0, st>>>(ngrd, ldgrd, nuse, d_tobs, d_wt, want_ot, t0use, d_test, d_t0, d_obj);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
 // locate_minLoc{Double64,Float64} (locate.c:811-851)
 // ------------------------------------------------------------------------------------------
 constexpr int kMinlocBlocks = 148 * 4;

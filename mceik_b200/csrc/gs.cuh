@@ -63,6 +63,11 @@ void launch_full_grid(int ngrd, size_t ldgrd, int nuse, const int *d_row, const 
 void launch_event_grid(int ngrd, size_t ldgrd, int npicks, const int *d_table_id, const double *d_tobs, const double *d_w_t0,
                        const double *d_w_obj, int want_ot, double t0use, const float *d_tables, double *d_logpdf,
                        float *d_logpdf4, double *d_t0, cudaStream_t st);
+// L1 flavour of the single-event search (locate.c:1205-1335): weighted-median origin time + weighted L1 misfit.
+// d_test holds the nuse used rows packed in pick order; d_wt the (normalised) weights.
+constexpr int kL1MaxObs = 128;
+void launch_l1_grid(int ngrd, size_t ldgrd, int nuse, const double *d_tobs, const double *d_wt, int want_ot, double t0use,
+                    const double *d_test, double *d_t0, double *d_obj, cudaStream_t st);
 // first index of the strict minimum (locate.c:811-851); result written to d_out[0]
 template <typename T>
 void launch_minloc(int n, const T *d_x, int *d_out, void *d_scratch, size_t scratch_bytes, cudaStream_t st,

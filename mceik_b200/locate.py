@@ -44,6 +44,23 @@ def locate_l2_gridSearch__float64(ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs,
         _ptr(tcorr, c_flt_p), _ptr(varobs, c_flt_p), _ptr(test, c_flt_p), _ptr(t0, c_flt_p), _ptr(objfn, c_flt_p))
 
 
+def locate_l1_gridSearch__double64(ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, varobs, test, t0, objfn):
+    """L1 flavour (locate.c:1205-1335): weighted-median origin time, weighted L1 misfit.  Returns the C return code."""
+    return _lib.load().locate_l1_gridSearch__double64(
+        int(ldgrd), int(ngrd), int(nobs), int(iwantOT), float(t0use), _ptr(mask, c_int_p), _ptr(tobs, c_dbl_p),
+        _ptr(varobs, c_dbl_p), _ptr(test, c_dbl_p), _ptr(t0, c_dbl_p), _ptr(objfn, c_dbl_p))
+
+
+def weightedMedian__double(x, w, perm=None):
+    """Host helper with the prototype of locate.c:73 -> (median, lsort, ierr); perm (int32 array) is updated in place."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    lsort, ierr = C.c_bool(False), C.c_int(0)
+    med = _lib.load().weightedMedian__double(x.size, _ptr(x, c_dbl_p), _ptr(w, c_dbl_p), _ptr(perm, c_int_p),
+                                             C.byref(lsort), C.byref(ierr))
+    return med, bool(lsort.value), ierr.value
+
+
 def locate_minLocDouble64(n, x):
     return _lib.load().locate_minLocDouble64(int(n), _ptr(x, c_dbl_p))
 

@@ -328,6 +328,76 @@ int oracle_event_logpdf(int job, int ngrd, size_t ldgrd, const float *tables, in
     return 0;
 }
 
+/* ---- L1 flavour: locate.c:1205-1335.  PARITY UNPINNED BY THE REFERENCE: weightedMedian__double is declared at
+ * locate.c:73 and defined nowhere, so the reference cannot link or run this function; only its demo inputs
+ * survive (locate.c:228-237).  The arithmetic restated here is the reference's; the median definition is the one
+ * written in include/mceik_b200.h, implemented independently of the product code (index sort, not pair insertion). */
+static const double *g_wm_x;
+static int wm_cmp(const void *a, const void *b)
+{
+    int ia = *(const int *)a, ib = *(const int *)b;
+    if (g_wm_x[ia] < g_wm_x[ib]) return -1;
+    if (g_wm_x[ia] > g_wm_x[ib]) return 1;
+    return ia < ib ? -1 : (ia > ib ? 1 : 0);
+}
+double oracle_weighted_median(int n, const double *x, const double *w)
+{
+    if (n < 1) return 0.0;
+    int *perm = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    g_wm_x = x;
+    qsort(perm, (size_t)n, sizeof(int), wm_cmp);
+    double W = 0.0, cum = 0.0, med = x[perm[n - 1]];
+    for (int k = 0; k < n; k++) W = W + w[perm[k]];
+    double half = 0.5 * W;
+    for (int k = 0; k < n; k++) {
+        cum = cum + w[perm[k]];
+        if (cum > half) { med = x[perm[k]]; break; }
+        if (cum == half) { med = k + 1 < n ? 0.5 * (x[perm[k]] + x[perm[k + 1]]) : x[perm[k]]; break; }
+    }
+    free(perm);
+    return med;
+}
+
+int oracle_l1_gridsearch_f64(int ldgrd, int ngrd, int nobs, int iwantOT, double t0use, const int *mask,
+                             const double *tobs, const double *varobs, const double *test, double *t0,
+                             double *objfn)
+{
+    if (ldgrd < ngrd || nobs < 1 || !mask || !tobs || !varobs || !test || !t0 || !objfn) return 1;
+    double *tc = (double *)malloc(sizeof(double) * (size_t)nobs);
+    double *wt = (double *)malloc(sizeof(double) * (size_t)nobs);
+    double *res = (double *)malloc(sizeof(double) * (size_t)nobs);
+    int *ptr = (int *)malloc(sizeof(int) * (size_t)nobs);
+    int nuse = 0;
+    double wtsum = 0.0;
+    for (int i = 0; i < nobs; i++) {           /* locate.c:1236-1246 */
+        if (mask[i] != 0) continue;
+        wt[nuse] = 1.0 / varobs[i];
+        tc[nuse] = tobs[i];
+        wtsum = wtsum + wt[nuse];
+        ptr[nuse++] = i;
+    }
+    for (int g = 0; g < ngrd; g++) objfn[g] = 0.0;
+    if (iwantOT == 1) {
+        if (fabs(wtsum - 1.0) > 1.e-14) {      /* locate.c:1263-1273 */
+            double wtsumi = 1.0 / wtsum;
+            for (int j = 0; j < nuse; j++) wt[j] = wt[j] * wtsumi;
+        }
+        for (int g = 0; g < ngrd; g++) {       /* locate.c:1284-1300 */
+            for (int j = 0; j < nuse; j++) res[j] = tc[j] - test[(size_t)ldgrd * (size_t)ptr[j] + g];
+            t0[g] = oracle_weighted_median(nuse, res, wt);
+        }
+    } else {
+        for (int g = 0; g < ngrd; g++) t0[g] = t0use;
+    }
+    for (int j = 0; j < nuse; j++) {           /* locate.c:1312-1324 */
+        const double *tt = test + (size_t)ldgrd * (size_t)ptr[j];
+        for (int g = 0; g < ngrd; g++) objfn[g] = objfn[g] + wt[j] * fabs(tc[j] - tt[g] - t0[g]);
+    }
+    free(tc); free(wt); free(res); free(ptr);
+    return 0;
+}
+
 /* ---- analytic homogeneous tables: homog.c:594-621 -------------------------------------
  * t[iz*nx*ny+iy*nx+ix] = sqrt((xs-x)^2+(ys-y)^2+(zs-z)^2) * (1/vel), x = x0 + ix*dx     */
 int oracle_homogeneous_traveltimes(int nx, int ny, int nz, double x0, double y0, double z0,

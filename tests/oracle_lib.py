@@ -195,3 +195,24 @@ def set_threads(n=0):
     L = lib()
     L.oracle_set_threads.restype = C.c_int
     return int(L.oracle_set_threads(C.c_int(int(n))))
+
+
+def weighted_median(x, w):
+    L = lib()
+    L.oracle_weighted_median.restype = C.c_double
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    return float(L.oracle_weighted_median(C.c_int(x.size), _p(x, c_dbl_p), _p(w, c_dbl_p)))
+
+
+def l1_gridsearch(ldgrd, ngrd, nobs, iwantOT, t0use, mask, tobs, varobs, test):
+    """L1 flavour (locate.c:1205-1335, parity unpinned) -> (rc, t0, objfn)."""
+    L = lib()
+    L.oracle_l1_gridsearch_f64.restype = C.c_int
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    tobs, varobs, test = (np.ascontiguousarray(a, dtype=np.float64) for a in (tobs, varobs, test))
+    t0, obj = np.zeros(ngrd), np.zeros(ngrd)
+    rc = L.oracle_l1_gridsearch_f64(C.c_int(ldgrd), C.c_int(ngrd), C.c_int(nobs), C.c_int(iwantOT), C.c_double(t0use),
+                                    _p(mask, c_int_p), _p(tobs, c_dbl_p), _p(varobs, c_dbl_p), _p(test, c_dbl_p),
+                                    _p(t0, c_dbl_p), _p(obj, c_dbl_p))
+    return rc, t0, obj

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "mceik_b200.h")
 def _declared_symbols():
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:mceik_|eikonal3d_|locate3d_|locate_|computeHomog)\w*)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b((?:mceik_|eikonal3d_|locate3d_|locate_|computeHomog|weightedMedian__)\w*)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():

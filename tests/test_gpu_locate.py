@@ -310,3 +310,32 @@ def test_pdf_helpers(gpu_ctx):
     zero = np.zeros(64)
     ierr, xsum = loc.normalize_pdf(zero)
     assert ierr == 1 and xsum == 0.0 and not zero.any()
+
+
+def test_l1_gridsearch_matches_oracle(gpu_ctx):
+    """L1 flavour (locate.c:1205-1335; parity unpinned by the reference, see include/mceik_b200.h): t0 and misfit
+    grids equal the oracle bit for bit; on the noise-free locate.c main case the weighted median is the origin
+    time and the misfit vanishes at the true node."""
+    from mceik_b200 import locate as L
+    c = refcases.locate_c_main_case()
+    n, ld, nobs = c["ngrd"], c["ldgrd"], c["nobs"]
+    t0, obj = np.zeros(n), np.zeros(n)
+    assert L.locate_l1_gridSearch__double64(ld, n, nobs, 1, 0.0, c["mask"], c["tobs"], c["varobs"], c["test"], t0, obj) == 0
+    rc, t0r, objr = O.l1_gridsearch(ld, n, nobs, 1, 0.0, c["mask"], c["tobs"], c["varobs"], c["test"])
+    assert rc == 0 and np.array_equal(t0, t0r) and np.array_equal(obj, objr)
+    iopt = L.locate_minLocDouble64(n, obj)
+    assert iopt == c["true_index"] and abs(t0[iopt] - 4.0) < 1e-9 and obj[iopt] < 1e-9
+    # noisy picks, unequal variances, masked picks, ties between residuals; then the fixed-t0 branch
+    rng = np.random.default_rng(3)
+    nobs, n = 23, 4097
+    ld = 4104
+    test = rng.uniform(0.5, 9.0, (nobs, ld)).round(2)            # two decimals: many equal residuals
+    tobs = (test[:, 1234] + 3.0 + rng.normal(0, 0.05, nobs)).round(2)
+    var = rng.choice([0.1, 0.25, 0.5, 1.0], nobs)
+    mask = (rng.uniform(size=nobs) < 0.2).astype(np.int32)
+    for want, t0use in ((1, 0.0), (0, 2.5)):
+        t0, obj = np.zeros(n), np.zeros(n)
+        assert L.locate_l1_gridSearch__double64(ld, n, nobs, want, t0use, mask, tobs, var, test.ravel(), t0, obj) == 0
+        rc, t0r, objr = O.l1_gridsearch(ld, n, nobs, want, t0use, mask, tobs, var, test.ravel())
+        assert rc == 0 and np.array_equal(t0, t0r) and np.array_equal(obj, objr)
+    assert L.locate_l1_gridSearch__double64(n - 1, n, nobs, 1, 0.0, mask, tobs, var, test.ravel(), t0, obj) == 1

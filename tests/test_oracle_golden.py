@@ -192,3 +192,45 @@ def test_homogeneous_tables_match_numpy():
     t = O.homogeneous_traveltimes(9, 8, 7, 0.0, 0.0, 0.0, 100.0, 100.0, 100.0, 250.0, 330.0, 600.0, 2000.0)
     ref = cases.homog_tables(9, 8, 7, 100.0, [250.0], [330.0], [600.0], 2000.0)[0]
     assert np.array_equal(t.astype(np.float32), ref)
+
+
+def _wmed_numpy(x, w):
+    """Independent statement of the weighted median of include/mceik_b200.h."""
+    order = np.lexsort((np.arange(x.size), x))
+    cum = np.cumsum(w[order])
+    half = 0.5 * cum[-1]
+    k = int(np.argmax(cum >= half))
+    if cum[k] == half and k + 1 < x.size:
+        return 0.5 * (x[order[k]] + x[order[k + 1]])
+    return x[order[k]]
+
+
+def test_weighted_median_definition():
+    """The reference only declares its weighted median (locate.c:73); its demo inputs (locate.c:228-237) give
+    0.2 with weights = values and the ordinary median 0.1 with unit weights.  Oracle == numpy statement ==
+    the host helper the library exports under the reference's name."""
+    from mceik_b200 import locate as L
+    xs = np.array([0.1, 0.35, 0.05, 0.1, 0.15, 0.05, 0.2])
+    assert O.weighted_median(xs, xs) == 0.2
+    assert O.weighted_median(xs, np.ones(7)) == 0.1
+    assert O.weighted_median(np.array([1.0, 4.0, 2.0, 3.0]), np.ones(4)) == 2.5      # even count: mean of the middle pair
+    assert O.weighted_median(np.array([5.0]), np.array([2.0])) == 5.0
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 8, 33, 100):
+        for _ in range(20):
+            x = rng.normal(size=n).round(1)
+            w = rng.choice([0.25, 0.5, 1.0, 2.0], n)
+            ref = _wmed_numpy(x, w)
+            assert O.weighted_median(x, w) == ref
+            perm = np.arange(n, dtype=np.int32)
+            med, lsort, ierr = L.weightedMedian__double(x, w, perm)
+            assert med == ref and ierr == 0 and lsort == bool(np.any(np.diff(x) < 0))
+            med2, lsort2, _ = L.weightedMedian__double(x, w, perm)     # the ordering is kept: no second sort
+            assert med2 == ref and not lsort2
+
+
+def test_l1_oracle_noise_free_case():
+    """L1 oracle on the locate.c main inputs: weighted-median t0 = 4 and zero misfit at the true node."""
+    c = refcases.locate_c_main_case()
+    rc, t0, obj = O.l1_gridsearch(c["ldgrd"], c["ngrd"], c["nobs"], 1, 0.0, c["mask"], c["tobs"], c["varobs"], c["test"])
+    assert rc == 0 and int(np.argmin(obj)) == c["true_index"] and abs(t0[c["true_index"]] - 4.0) < 1e-9
