@@ -232,7 +232,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.nfields_active = (int)active.size();
             // few fields: short publication interval (tight pipelining of the brick wavefront);
             // many fields: parallelism is plentiful, publish less often (each publication costs a fence)
-            a.publish = active.size() >= 48 ? 16 : 8;  // measured at 16/32/64/128 fields (profiles/kernel_evolution_r1.md)
+            a.publish = active.size() >= 48 ? 16 : (active.size() >= 12 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
             if (const char *e = getenv("MCEIK_FSM_PUBLISH")) a.publish = atoi(e);
             a.h = g->h;
             a.active = d_active; a.field_model = d_fmodel; a.slow = d_slow; a.u = d_u;

@@ -75,7 +75,7 @@ struct BrickArgs {
     int nx, ny, nz;
     int nbx, nby, nbz, nbricks, nblevels, zc, by;
     int nfields_active;
-    int publish;              // a sweeping warp publishes its progress every `publish` steps (8 or 16; a power of two)
+    int publish;              // a sweeping warp publishes its progress every `publish` steps (4, 8 or 16; a power of two)
     double h;
     const int *active;        // [nfields_active] field ids
     const int *field_model;   // [nfields]
