@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         auto wait_upwind = [&](int steps_needed) {
             const long long t0 = a.stats ? clock64() : 0;
             if (up_ptr) {
-                const int need = (s << kProgShift) + steps_needed;
+                // lane 0 watches the upwind x neighbour, lane 1 the upwind y neighbour.  A slot's y-halo row is the
+                // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
+                // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
+                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? kBy - 2 : 0);
                 while (ld_acquire_gpu(up_ptr) < need) __nanosleep(200);
             }
             __syncwarp();
