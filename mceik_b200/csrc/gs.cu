@@ -342,24 +342,61 @@ __global__ void __launch_bounds__(kThreads, 2) locate_uniform_kernel(const Locat
                     double T[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) T[r] = (double)Tc[jj][r];  // DBLE(test4), locate.f90:414,459
+                    // the (tobs, weight) constants of kCB events are fetched together and their kCB * R update
+                    // chains are written stage by stage, so neither the shared-memory latency nor the fp64
+                    // latency of one chain is exposed (each event/node chain keeps its own operation order)
                     const double2 *c = s_c + (size_t)(j0 + jj) * EB;
+                    constexpr int kCB = 4;
+                    static_assert(EB % kCB == 0, "event block must be a multiple of the constant batch");
                     if (pass == 0) {
 #pragma unroll
-                        for (int e = 0; e < EB; ++e) {
-                            const double2 cw = c[e];
+                        for (int e0b = 0; e0b < EB; e0b += kCB) {
+                            double2 cw[kCB];
+                            double d[kCB][R];
 #pragma unroll
-                            for (int r = 0; r < R; ++r)  // locate.c:409
-                                t0[e][r] = __dadd_rn(t0[e][r], __dmul_rn(cw.y, __dsub_rn(cw.x, T[r])));
+                            for (int q = 0; q < kCB; ++q) cw[q] = c[e0b + q];
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dsub_rn(cw[q].x, T[r]);
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dmul_rn(cw[q].y, d[q][r]);
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r)  // locate.c:409
+                                    t0[e0b + q][r] = __dadd_rn(t0[e0b + q][r], d[q][r]);
                         }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < EB; ++e) {
-                            const double2 cw = c[e];
+                        for (int e0b = 0; e0b < EB; e0b += kCB) {
+                            double2 cw[kCB];
+                            double d[kCB][R];
 #pragma unroll
-                            for (int r = 0; r < R; ++r) {  // locate.c:511-512
-                                const double res = __dmul_rn(cw.y, __dsub_rn(cw.x, __dadd_rn(T[r], t0[e][r])));
-                                obj[e][r] = __dadd_rn(obj[e][r], __dmul_rn(res, res));
-                            }
+                            for (int q = 0; q < kCB; ++q) cw[q] = c[e0b + q];
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dadd_rn(T[r], t0[e0b + q][r]);
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dsub_rn(cw[q].x, d[q][r]);
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dmul_rn(cw[q].y, d[q][r]);  // locate.c:511
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r) d[q][r] = __dmul_rn(d[q][r], d[q][r]);
+#pragma unroll
+                            for (int q = 0; q < kCB; ++q)
+#pragma unroll
+                                for (int r = 0; r < R; ++r)  // locate.c:512
+                                    obj[e0b + q][r] = __dadd_rn(obj[e0b + q][r], d[q][r]);
                         }
                     }
                 }
