@@ -48,6 +48,11 @@ struct mceik_ctx {
     double last_sweep_ms = 0.0;
     int last_sweep_launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // mceik_fsm_solve_batched_host with pinned output: a converged field is copied back on copy_stream while
+    // the remaining fields keep iterating (early_u = host destination, early_done[f] = already on its way)
+    cudaStream_t copy_stream = nullptr;
+    double *early_u = nullptr;
+    std::vector<char> early_done;
     fsm::TilePlan plan;
     fsm::BrickPlan bplan;
     int brick_zc = 256, brick_by = 8;
@@ -307,6 +312,15 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             it[f] = k;
             if (h_nonconv[f] != 0) still.push_back(f);  // lconv /= nxyz -> next iteration (fsm3d.f90:95)
         }
+        if (ctx->early_u) {  // the stream is idle here (synchronised above), so a field that just converged is final
+            size_t j = 0;
+            for (int f : active) {
+                if (j < still.size() && still[j] == f) { ++j; continue; }
+                MCEIK_CUDA(cudaMemcpyAsync(ctx->early_u + (size_t)f * N, d_u + (size_t)f * N, sizeof(double) * N,
+                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+                ctx->early_done[f] = 1;
+            }
+        }
         active.swap(still);
     }
     int rc = 0;
@@ -443,6 +457,7 @@ void mceik_ctx_destroy(mceik_ctx *c) {
             b->release();
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     } catch (...) {
     }
@@ -518,10 +533,36 @@ int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int
         double *d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * std::max(nfields, 1)));
         float *d_tab = nullptr;
         if (tables) d_tab = static_cast<float *>(ctx->ws_tab.ensure(sizeof(float) * ldtab * std::max(nfields, 1)));
-        const int rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nfields, field_model, src_ptr, ts, xs, ys, zs, d_u, d_tab,
-                                     ldtab, iters, field_ierr);
+        // pinned destination: copy every field back as soon as it has converged, overlapped with the sweeps of
+        // the others (pageable memory would make those copies block the host between iterations)
+        cudaPointerAttributes pa{};
+        const bool pinned = u && nfields > 1 && cudaPointerGetAttributes(&pa, u) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        ctx->early_u = nullptr;
+        if (pinned) {
+            if (!ctx->copy_stream) MCEIK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            ctx->early_u = u;
+            ctx->early_done.assign(nfields, 0);
+        }
+        int rc;
+        try {
+            rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nfields, field_model, src_ptr, ts, xs, ys, zs, d_u, d_tab, ldtab, iters,
+                               field_ierr);
+        } catch (...) {
+            ctx->early_u = nullptr;
+            throw;
+        }
+        ctx->early_u = nullptr;
         if (rc < 0) return rc;
-        if (u) MCEIK_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToHost, ctx->stream));
+        if (u && pinned) {
+            for (int f = 0; f < nfields; ++f)  // fields that stopped at maxit or failed their boundary conditions
+                if (!ctx->early_done[f])
+                    MCEIK_CUDA(cudaMemcpyAsync(u + (size_t)f * N, d_u + (size_t)f * N, sizeof(double) * N, cudaMemcpyDeviceToHost,
+                                               ctx->stream));
+            MCEIK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        } else if (u) {
+            MCEIK_CUDA(cudaMemcpyAsync(u, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         if (tables)
             MCEIK_CUDA(cudaMemcpyAsync(tables, d_tab, sizeof(float) * ldtab * nfields, cudaMemcpyDeviceToHost, ctx->stream));
         MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -111,14 +111,20 @@ class EikonalSolver:
         self.lib.mceik_fsm_last_sweep_stats(self.ctx.handle, C.byref(ms), C.byref(n))
         return ms.value, n.value
 
-    def solve_host(self, slow, field_model, ts, xs, ys, zs, src_ptr=None, want_u=True, want_tables=False, ldtab=None):
-        """Host (numpy) buffers in and out.  slow: [nmodels, N] fp64.  Returns (u, tables, iters, ierr)."""
+    def solve_host(self, slow, field_model, ts, xs, ys, zs, src_ptr=None, want_u=True, want_tables=False, ldtab=None,
+                   out_u=None):
+        """Host (numpy) buffers in and out.  slow: [nmodels, N] fp64.  Returns (u, tables, iters, ierr).
+        out_u: optional caller-owned [nfields, N] fp64 array for the fields; when it is page-locked, every field is
+        copied back as soon as it has converged, overlapped with the iterations of the others."""
         slow = np.ascontiguousarray(slow, dtype=np.float64).reshape(-1, self.n)
         field_model = np.ascontiguousarray(field_model, dtype=np.int32)
         nf = field_model.size
         ts, xs, ys, zs, src_ptr = self._sources(nf, ts, xs, ys, zs, src_ptr)
         ldtab = self.n if ldtab is None else int(ldtab)
         u = np.empty((nf, self.n), dtype=np.float64) if want_u else None
+        if out_u is not None:
+            assert out_u.dtype == np.float64 and out_u.flags.c_contiguous and out_u.size == nf * self.n
+            u = out_u
         tab = np.zeros((nf, ldtab), dtype=np.float32) if want_tables else None
         iters = np.zeros(nf, dtype=np.int32)
         ferr = np.zeros(nf, dtype=np.int32)

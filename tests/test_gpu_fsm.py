@@ -80,6 +80,32 @@ def test_batched_fields_two_models(gpu_ctx, algo):
     assert sol.node_updates == int(n * 8 * its.sum())
 
 
+def test_pinned_output_is_copied_back_as_fields_converge(gpu_ctx):
+    """Page-locked output: fields leave the device as soon as they converge (different iterations per field),
+    fields stopped by maxit or refused by the boundary conditions at the end; same bits as the pageable path."""
+    import torch
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 48, 40, 56, 250.0
+    n = nx * ny * nz
+    slow = np.stack([cases.checkerboard_slowness(nx, ny, nz, cell=8), cases.random_slowness(n, 3)])
+    fmodel = np.array([0, 1, 0, 0, 1, 0, 0, 1], dtype=np.int32)
+    xs, ys, zs = cases.interior_sources(8, nx, ny, nz, h, seed=11)
+    xs[5] = -10.0                                             # field 5: source outside the grid -> ierr 1
+    ts = np.linspace(0.0, 1.0, 8)
+    for maxit in (20, 3):
+        sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=maxit)
+        ref, _, iters_ref, ferr_ref = sol.solve_host(slow, fmodel, ts, xs, ys, zs)
+        pinned = torch.zeros((8, n), dtype=torch.float64).pin_memory()
+        u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, out_u=pinned.numpy())
+        assert list(ferr) == list(ferr_ref) and ferr[5] == 1 and np.array_equal(iters, iters_ref)
+        ok = ferr == 0
+        assert np.array_equal(u[ok], ref[ok])
+        if maxit == 20:
+            assert len(set(iters[ok])) > 1                    # the early copies really happen at different times
+            oracle, its = _oracle_fields(nx, ny, nz, h, slow, fmodel[:2], xs[:2], ys[:2], zs[:2], ts[:2], 1e-6, 20)
+            assert np.array_equal(u[:2], oracle) and np.array_equal(iters[:2], its)
+
+
 @pytest.mark.parametrize("algo", [0, 2])
 def test_c2_layered_128_bit_exact(gpu_ctx, algo):
     """BASELINE config 2: 128^3, 1-D layered model, one station."""
