@@ -262,7 +262,12 @@ __global__ void __launch_bounds__(kThreads, 2) locate_uniform_kernel(const Locat
     extern __shared__ __align__(16) unsigned char smem[];
     const int e0 = blockIdx.y * EB;
     if (!a.blk_uniform[blockIdx.y]) return;  // mixed tables per slot: handled by locate_kernel
-    const int P = (a.maxpicks + 3) & ~3;
+    // slots walked by this block: the longest pick list of its own events (shared memory is sized for a.maxpicks)
+    int pblk = 0;
+#pragma unroll
+    for (int e = 0; e < EB; ++e)
+        if (e0 + e < a.nevents) pblk = max(pblk, a.obs_ptr[e0 + e + 1] - a.obs_ptr[e0 + e]);
+    const int P = (min(pblk, a.maxpicks) + 3) & ~3;
     double2 *s_a = reinterpret_cast<double2 *>(smem);  // [P][EB] (tobs, w_t0)
     double2 *s_b = s_a + (size_t)EB * P;               // [P][EB] (tobs, w_obj)
     int *s_id = reinterpret_cast<int *>(s_b + (size_t)EB * P);  // [P] table of the slot

@@ -204,6 +204,55 @@ def test_batched_ragged_catalog(gpu_ctx):
             assert ob[0] == obj[e] and hy[3] == t0[e]
 
 
+def test_ragged_sorted_catalog_is_aligned_onto_the_fast_kernel(gpu_ctx):
+    """Events with different subsets of the tables, picks in increasing table order (a station-ordered catalogue):
+    the host entry re-lays each block of 8 events out over the union of its tables so the branch-free kernel runs it;
+    results are the same bits as the general kernel (alignment switched off) and as the oracle, event by event."""
+    import os
+    from mceik_b200.locate import Locator
+    n, h, tables, _ = _c1_case(nevents=1, n=24, nstat=9)
+    ngrd = n ** 3
+    ntab = tables.shape[0]
+    rng = np.random.default_rng(123)
+    ne = 45
+    obs_ptr, tid, tc, var, tori = [0], [], [], [], rng.uniform(0, 5, ne)
+    for e in range(ne):
+        k = 0 if e == 11 else int(rng.integers(1, ntab + 1))
+        ids = np.sort(rng.permutation(ntab)[:k])
+        if e == 20:
+            ids = ids[::-1]                      # one block that is not in table order -> stays on the general kernel
+        node = int(rng.integers(0, ngrd))
+        for t in ids:
+            used = rng.random() > 0.15
+            tid.append(int(t) if used else -1)
+            tc.append(float(tables[t, node]) + tori[e] + rng.normal(0, 0.02))
+            var.append(float(rng.choice([0.1, 0.25, 0.5])))
+        obs_ptr.append(len(tid))
+    obs_ptr, tid, tc, var = np.array(obs_ptr, np.int32), np.array(tid, np.int32), np.array(tc), np.array(var)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    for job in (2, 1):
+        iopt, t0, obj = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
+        os.environ["MCEIK_LOCATE_NO_ALIGN"] = "1"
+        try:
+            iopt_g, t0_g, obj_g = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
+        finally:
+            os.environ.pop("MCEIK_LOCATE_NO_ALIGN")
+        assert np.array_equal(iopt, iopt_g) and np.array_equal(t0, t0_g) and np.array_equal(obj, obj_g)
+        for e in range(ne):
+            b, en = obs_ptr[e], obs_ptr[e + 1]
+            k = en - b
+            use = (tid[b:en] >= 0).astype(np.int32)
+            if use.sum() == 0:
+                assert iopt[e] == -1
+                continue
+            stat = np.where(use == 1, tid[b:en] // 2 + 1, 1).astype(np.int32)
+            ph = np.where(use == 1, tid[b:en] % 2 + 1, 1).astype(np.int32)
+            rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, k, 1, use, stat, ph, np.zeros(k), tori[e:e + 1],
+                                                var[b:en], tc[b:en], np.zeros(ngrd), np.zeros(ngrd), np.zeros(ngrd))
+            assert rc == 0 and io[0] == iopt[e] and ob[0] == obj[e] and hy[3] == t0[e], f"event {e}"
+
+
 def test_catalog_struct_entry(gpu_ctx):
     """mceik_locate_catalog with the mceik_struct.h layouts (CSR obsPtr, 1-based statPtr, P/S corrections)."""
     from mceik_b200.locate import Locator
