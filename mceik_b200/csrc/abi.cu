@@ -57,7 +57,7 @@ struct mceik_ctx {
     fsm::BrickPlan bplan;
     int brick_zc = 256, brick_by = 8;
     // eikonal workspaces
-    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv;
+    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh;
     // locator state
     const float *d_tables = nullptr;
     DevBuf own_tables;
@@ -212,6 +212,14 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     unsigned long long *d_nonconv = reinterpret_cast<unsigned long long *>(ctrl + c_nonconv);
     std::vector<unsigned long long> h_nonconv(nfields);
 
+    // the 16-byte-pair brick kernel reads slow*h, formed once per solve instead of once per node visit
+    const bool bricks16 = bricks && nx % 8 == 0 && bp.by == 8 && !getenv("MCEIK_FSM_NO16");
+    const double *d_fh = nullptr;
+    if (bricks16) {
+        double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * N * nmodels));
+        fsm::launch_scale_slowness(N * nmodels, g->h, d_slow, fh, st);
+        d_fh = fh;
+    }
     if (bricks)  // u0 = u before the first iteration (fsm3d.f90:60); refreshed by the convergence kernel
         MCEIK_CUDA(cudaMemcpyAsync(d_u0, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToDevice, st));
     uint8_t *d_lupd = nullptr;
@@ -240,7 +248,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.publish = active.size() >= 48 ? 16 : (active.size() >= 12 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
             if (const char *e = getenv("MCEIK_FSM_PUBLISH")) a.publish = atoi(e);
             a.h = g->h;
-            a.active = d_active; a.field_model = d_fmodel; a.slow = d_slow; a.u = d_u;
+            a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
+            a.u = d_u;
             a.brick_order = ctx->bplan.brick_order.as<int>();
             a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);
@@ -250,7 +259,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.stats = getenv("MCEIK_FSM_STATS") ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
             MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
-            if (nx % 8 == 0 && a.by == 8 && !getenv("MCEIK_FSM_NO16")) fsm::launch_iteration_bricks16(a, st);
+            if (bricks16) fsm::launch_iteration_bricks16(a, st);
             else fsm::launch_iteration_bricks(a, st);
             MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
             ctx->last_sweep_launches += 1;
@@ -452,7 +461,7 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         cudaStreamSynchronize(c->stream);
         c->plan.release();
         c->bplan.release();
-        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv,
+        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
         if (c->ev0) cudaEventDestroy(c->ev0);

@@ -466,6 +466,17 @@ void launch_convergence(size_t n, int nfields, const int *d_active_fields, doubl
     MCEIK_LAUNCH_CHECK();
 }
 
+__global__ void scale_slowness_kernel(size_t n, double h, const double *__restrict__ slow, double *__restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __dmul_rn(slow[i], h);
+}
+
+void launch_scale_slowness(size_t n, double h, const double *d_slow, double *d_out, cudaStream_t st) {
+    if (n == 0) return;
+    scale_slowness_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(n, h, d_slow, d_out);
+    MCEIK_LAUNCH_CHECK();
+}
+
 __global__ void mark_bcs_kernel(int nrec, const int *__restrict__ rec_field, const int *__restrict__ rec_node,
                                 size_t n, uint8_t *__restrict__ lupd) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -79,7 +79,8 @@ struct BrickArgs {
     double h;
     const int *active;        // [nfields_active] field ids
     const int *field_model;   // [nfields]
-    const double *slow;       // [nmodels][N]
+    const double *slow;       // [nmodels][N]; bricks16: slow*h (slow_is_fh), the product UPDATE3D forms per visit
+    int slow_is_fh;
     double *u;                // [nfields][N]
     const int *brick_order;
     const int *blevel_ptr;
@@ -97,6 +98,8 @@ void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st);
 // device self-test of sqrt_fast / local_solve_sl against __dsqrt_rn / local_solve; d_bad[2] counts mismatches
 void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st);
 void launch_fill(double *d_u, size_t n, double value, cudaStream_t st);
+// d_out[i] = d_slow[i] * h (fsm3d.f90:470 evaluates this product at every node visit; same bits every time)
+void launch_scale_slowness(size_t n, double h, const double *d_slow, double *d_out, cudaStream_t st);
 // One thread per field applies its BcRecords in source order.
 void launch_apply_bcs(int nfields, size_t n, const int *d_field_model, const int *d_rec_ptr,
                       const BcRecord *d_recs, const double *d_slow, double *d_u, cudaStream_t st);

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 ux[c] = dmin2(pxm[c * kURow], pxp[c * kURow]);
                 uy[c] = dmin2(pm[(c - 1) * kURow], pp[(c + 1) * kURow]);
                 uz[c] = dmin2(zm[c], zp[c]);
-                fh[c] = __dmul_rn(U[oc + cf0 + c * kBx], a.h);
+                fh[c] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
             }
             local_solve_xn<kNC>(ux, uy, uz, fh, go, nv);
 #pragma unroll
@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
 void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
     if (a.nfields_active == 0) return;
     if (a.zc < 1 || a.zc > kMaxZc || a.by != kBy || a.nx % kBx != 0) throw CudaError("bricks16: unsupported geometry");
+    if (!a.slow_is_fh) throw CudaError("bricks16: expects the slowness premultiplied by h");
     const size_t smem = kWarpSmem * kWarps;
     MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 0;
