@@ -182,7 +182,7 @@ def run_reference(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_gs_sample(ngrd, tables_host, cat, nevents, cores):
@@ -350,7 +350,7 @@ def run_ours(a):
                 "dtype": "f64", "data": "synthetic", "config": dict(workload_config(a, world), iterations_per_field=iters),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "events": events}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -463,7 +463,16 @@ def run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, d_u, d_
             "gpu_launches": int(launches)}
 
 
+def emit(line):
+    """The one JSON line of the contract, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # Libraries (NCCL prints its version banner) write to fd 1: keep the real stdout for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
