@@ -66,6 +66,7 @@ struct BrickPlan {
     int nbx = 0, nby = 0, nbz = 0, nbricks = 0, nblevels = 0;
     DevBuf brick_order;  // int[nbricks]: I | J<<10 | K<<20 sorted by I+J+K
     DevBuf blevel_ptr;   // int[nblevels+1]
+    std::vector<int> h_blevel_ptr;  // host copy (ticket tables are built per launch)
     void build(int nx_, int ny_, int nz_, int by_, int zc_, cudaStream_t st);
     void release();
 };
@@ -86,6 +87,11 @@ struct BrickArgs {
     const int *blevel_ptr;
     int *done;                    // [nfields][nbricks] sweeps completed per brick, zeroed per launch
     unsigned long long *queue;    // [1] ticket counter, zeroed per launch
+    // bricks16 ticket order: the active fields form two groups; group 1 runs `stagger` brick levels behind group 0,
+    // so one group is in the wide middle of a sweep while the other ramps up or drains.  Virtual level V holds
+    // (sweep, level) = divmod(V, nblevels) of group 0 and divmod(V - stagger, nblevels) of group 1.
+    const long long *vptr;        // [8 * nblevels + stagger + 1] tickets before virtual level V
+    int nf0, stagger;             // group 0 = active[0, nf0), group 1 = active[nf0, nfields_active)
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
     const int *bc_node;           // flat node index of each (unique) boundary-condition node
     unsigned long long *stats;    // optional [4] cycle counters (MCEIK_FSM_STATS=1), else nullptr

@@ -446,6 +446,7 @@ void BrickPlan::build(int nx_, int ny_, int nz_, int by_, int zc_, cudaStream_t 
             }
     }
     ptr[nblevels] = (int)order.size();
+    h_blevel_ptr = ptr;
     MCEIK_CUDA(cudaMemcpyAsync(brick_order.ensure(sizeof(int) * nbricks), order.data(), sizeof(int) * nbricks,
                                cudaMemcpyHostToDevice, st));
     MCEIK_CUDA(cudaMemcpyAsync(blevel_ptr.ensure(sizeof(int) * (nblevels + 1)), ptr.data(), sizeof(int) * (nblevels + 1),
