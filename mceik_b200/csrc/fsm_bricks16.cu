@@ -217,27 +217,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         }
 
         int ld_slot = 0, ld_m = 0;
+        // steady steps form every global address as (per-task byte base) + zo, one running plane offset in bytes
+        const long long zsb = zstride * (long long)sizeof(double);
+        long long zo = -(long long)kofs_t * zsb;                            // (ld_m - kofs_t) planes
+        const char *bu_t = reinterpret_cast<const char *>(pu_t), *bf_t = reinterpret_cast<const char *>(pf_t);
+        const char *bu_h = reinterpret_cast<const char *>(pu_h) + (long long)(kofs_t - kofs_h) * zsb;  // halo pair of the same issue
+        char *bu_st = reinterpret_cast<char *>(pu_t) - 10 * zsb;           // pair written back in the same step
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
             const int k = ld_m - kofs_t;
             if (kSteady) {
-                const long long z = (long long)k * zstride;
-                cp_async16(sp + cu_t, pu_t + z);
-                cp_async16(sp + cf_t, pf_t + z);
+                cp_async16(sp + cu_t, bu_t + zo);
+                cp_async16(sp + cf_t, bf_t + zo);
             } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
                 const long long z = (long long)min(max(k, klo), khi) * zstride;
                 cp_async16(sp + cu_t, pu_t + z);
                 if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + z);
             }
             const int kh = ld_m - kofs_h;
-            if (hmode == 1) {
-                if (kSteady || (kh >= 0 && kh < ez)) cp_async16(sp + cu_h, pu_h + (long long)kh * zstride);
+            if (kSteady) {  // full brick off the x faces: every halo lane copies a pair
+                if (hmode != 0) cp_async16(sp + cu_h, bu_h + zo);
+            } else if (hmode == 1) {
+                if (kh >= 0 && kh < ez) cp_async16(sp + cu_h, pu_h + (long long)kh * zstride);
             } else if (hmode == 2) {
                 if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * zstride);
             }
             cp_async_commit();
             ++ld_m;
+            zo += zsb;
             ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
         };
         for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot(std::false_type());
@@ -312,7 +320,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 const int ks = l - 3 - kofs_t;
                 if (kSteady || (act_t && (unsigned)ks < (unsigned)ez)) {
                     const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + cu_t);
-                    __stcg(reinterpret_cast<double2 *>(pu_t + (long long)ks * zstride), v);
+                    if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st + zo), v);
+                    else __stcg(reinterpret_cast<double2 *>(pu_t + (long long)ks * zstride), v);
                 }
             }
             om = oc; oc = op;
