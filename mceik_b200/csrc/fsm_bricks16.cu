@@ -298,10 +298,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             const double *pxm = (xm_prev ? pm : pc) - sx, *pxp = (xp_next ? pp : pc) + sx;
             double ux[kNC], uy[kNC], uz[kNC], fh[kNC], zp[kNC], nv[kNC];
 #pragma unroll
+            for (int c = 0; c < kNC; ++c) zp[c] = pp[c * kURow];
+#pragma unroll
             for (int c = 0; c < kNC; ++c) {
-                zp[c] = pp[c * kURow];
                 ux[c] = dmin2(pxm[c * kURow], pxp[c * kURow]);
-                uy[c] = dmin2(pm[(c - 1) * kURow], pp[(c + 1) * kURow]);
+                // the lane's own column supplies two of the y neighbours from registers: row j0+c-1 one plane back is
+                // what the lane wrote (or kept) for its node c-1 in the previous step, row j0+c+1 is zp of node c+1
+                const double ym = c > 0 ? zm[c - 1] : pm[(c - 1) * kURow];
+                const double yp = c + 1 < kNC ? zp[c + 1] : pp[(c + 1) * kURow];
+                uy[c] = dmin2(ym, yp);
                 uz[c] = dmin2(zm[c], zp[c]);
                 fh[c] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
             }
