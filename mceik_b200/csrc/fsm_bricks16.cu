@@ -126,6 +126,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby) up_ptr = done_f + ((K * a.nby + NJ) * a.nbx + NI);
         }
         long long t_upwind = 0;
+        // progress of the watched neighbour: `seen` = highest value observed so far (it only grows), `ahead` = an
+        // observation issued one chunk earlier whose latency is hidden behind that chunk's arithmetic
+        int seen = 0, ahead = 0;
         auto wait_upwind = [&](int steps_needed) {
             const long long t0 = a.stats ? clock64() : 0;
             if (up_ptr) {
@@ -133,7 +136,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
                 const int need = (s << kProgShift) + steps_needed - (lane == 0 ? kBy - 2 : 0);
-                while (ld_acquire_gpu(up_ptr) < need) __nanosleep(200);
+                seen = max(seen, ahead);
+                if (seen < need)
+                    while ((seen = ld_acquire_gpu(up_ptr)) < need) __nanosleep(200);
+                if (seen < ((s + 1) << kProgShift)) ahead = ld_acquire_gpu(up_ptr);  // consumed at the next chunk
             }
             __syncwarp();
             if (a.stats) t_upwind += clock64() - t0;
