@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         long long zo = -(long long)kofs_t * zsb;                            // (ld_m - kofs_t) planes
         const char *bu_t = reinterpret_cast<const char *>(pu_t), *bf_t = reinterpret_cast<const char *>(pf_t);
         const char *bu_h = reinterpret_cast<const char *>(pu_h) + (long long)(kofs_t - kofs_h) * zsb;  // halo pair of the same issue
-        char *bu_st = reinterpret_cast<char *>(pu_t) - 10 * zsb;           // pair written back in the same step
+        char *bu_st = reinterpret_cast<char *>(pu_t) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
