@@ -246,7 +246,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.nfields_active = (int)active.size();
             // few fields: short publication interval (tight pipelining of the brick wavefront);
             // many fields: parallelism is plentiful, publish less often (each publication costs a fence)
-            a.publish = active.size() >= 48 ? 16 : (active.size() >= 12 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
+            a.publish = active.size() >= 48 ? 16 : (active.size() > 16 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
             if (const char *e = getenv("MCEIK_FSM_PUBLISH")) a.publish = atoi(e);
             a.h = g->h;
             a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
@@ -257,6 +257,10 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
             a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0;
+            // few active fields: a publisher warp per CTA takes the release fences off the sweeping warps (+8-12 % up to
+            // 11 fields, +1 % at 16, nothing beyond; profiles/kernel_evolution_r1.md)
+            a.publisher = active.size() <= 16 ? 1 : 0;
+            if (const char *e = getenv("MCEIK_FSM_PUBLISHER")) a.publisher = atoi(e) != 0;
             if (bricks16) {  // two field groups half a sweep apart (see BrickArgs)
                 const int nl = bp.nblevels, nfa = a.nfields_active;
                 a.nf0 = (nfa + 1) / 2;

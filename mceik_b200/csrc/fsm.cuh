@@ -92,6 +92,7 @@ struct BrickArgs {
     // (sweep, level) = divmod(V, nblevels) of group 0 and divmod(V - stagger, nblevels) of group 1.
     const long long *vptr;        // [8 * nblevels + stagger + 1] tickets before virtual level V
     int nf0, stagger;             // group 0 = active[0, nf0), group 1 = active[nf0, nfields_active)
+    int publisher;                // bricks16: 1 = the last warp of every CTA publishes progress for the others
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
     const int *bc_node;           // flat node index of each (unique) boundary-condition node
     unsigned long long *stats;    // optional [4] cycle counters (MCEIK_FSM_STATS=1), else nullptr

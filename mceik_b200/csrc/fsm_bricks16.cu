@@ -51,11 +51,90 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ int xgroup(int i) { return (i + 4) >> 2; }
 
+// Publisher variant (few active fields: the release fence of a publication, not the arithmetic, is what a sweeping
+// warp waits for).  The last warp of the CTA sweeps nothing: it takes (progress word, value) requests from the other
+// warps through shared memory, executes one gpu-scope fence for all pending requests and stores the values.  The
+// hand-off is a cta-scope release / acquire, so the sweeping warp's stores happen-before the publisher's fence and
+// its relaxed store completes a (cumulative) gpu-scope release pattern -- the same guarantee as st.release.gpu by
+// the sweeping warp itself, minus the stall.
+struct Mail {
+    unsigned long long req;  // (sequence << 32) | value, written with st.release.cta
+    unsigned int ack;        // last sequence the publisher has stored, written with st.release.cta
+    int *ptr;                // progress word of the request; changes only when ack == sequence
+};
+__device__ __forceinline__ unsigned long long ld_acquire_cta_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.cta.shared.u64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_cta_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(int *p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 }  // namespace
 
+template <bool kPub>
 __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ Mail mail[kWarps];
+    __shared__ unsigned int workers_done;
+    constexpr int kWorkers = kPub ? kWarps - 1 : kWarps;
+    unsigned int my_seq = 0;  // lane 0 of a sweeping warp: sequence of its last request
+    if (kPub) {
+        if (threadIdx.x < kWarps) { mail[threadIdx.x].req = 0ULL; mail[threadIdx.x].ack = 0u; mail[threadIdx.x].ptr = nullptr; }
+        if (threadIdx.x == 0) workers_done = 0u;
+        __syncthreads();
+        if (warp == kWarps - 1) {  // ---- the publisher
+            unsigned int last = 0;  // lane w: last sequence stored for sweeping warp w
+            while (true) {
+                const unsigned int fin = ld_acquire_cta_u32(&workers_done);  // read BEFORE the requests: a warp posts, then finishes
+                unsigned long long r = 0ULL;
+                bool pend = false;
+                if (lane < kWorkers) {
+                    r = ld_acquire_cta_u64(&mail[lane].req);
+                    pend = (unsigned int)(r >> 32) != last;
+                }
+                if (__any_sync(0xffffffffu, pend)) {
+                    __threadfence();  // fence.sc.gpu >= acq_rel: everything the acquired requests cover is performed gpu-wide
+                    if (pend) {
+                        st_relaxed_gpu(mail[lane].ptr, (int)(unsigned int)r);
+                        last = (unsigned int)(r >> 32);
+                        st_release_cta_u32(&mail[lane].ack, last);
+                    }
+                } else {
+                    if (fin == (unsigned int)kWorkers) break;
+                    __nanosleep(64);
+                }
+            }
+            return;
+        }
+    }
+    // progress publication of a sweeping warp (lane 0 only, after __syncwarp)
+    auto publish_progress = [&](int *ptr, int val) {
+        if (kPub) {
+            Mail &m = mail[warp];
+            if (m.ptr != ptr) {  // a request for another brick may still be on its way: let it go out first
+                while (ld_acquire_cta_u32(&m.ack) != my_seq) __nanosleep(32);
+                m.ptr = ptr;
+            }
+            ++my_seq;
+            st_release_cta_u64(&m.req, ((unsigned long long)my_seq << 32) | (unsigned int)val);
+        } else {
+            st_release_gpu(ptr, val);
+        }
+    };
     double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
     unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc]
 
@@ -344,7 +423,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         auto publish_chunk = [&](int l1) {
             if (l1 < nsteps) {
                 __syncwarp();
-                if (lane == 0) st_release_gpu(done_f + brick, (s << kProgShift) + l1);
+                if (lane == 0) publish_progress(done_f + brick, (s << kProgShift) + l1);
             }
         };
         auto step = [&](int l) {
@@ -369,7 +448,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
 
         cp_async_wait<0>();
         __syncwarp();
-        if (lane == 0) st_release_gpu(done_f + brick, (s + 1) << kProgShift);
+        if (lane == 0) publish_progress(done_f + brick, (s + 1) << kProgShift);
         __syncwarp();
         if (a.stats && lane == 0) {
             const long long t_end = clock64();
@@ -379,6 +458,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             atomicAdd(a.stats + 3, 1ULL);
         }
     }
+    if (kPub && lane == 0) {  // the last request is posted before the count goes up; the publisher reads them in the opposite order
+        __threadfence_block();
+        atomicAdd(&workers_done, 1u);
+    }
 }
 
 void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
@@ -386,13 +469,19 @@ void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
     if (a.zc < 1 || a.zc > kMaxZc || a.by != kBy || a.nx % kBx != 0) throw CudaError("bricks16: unsupported geometry");
     if (!a.slow_is_fh) throw CudaError("bricks16: expects the slowness premultiplied by h");
     const size_t smem = kWarpSmem * kWarps;
-    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, nsm = 0;
     MCEIK_CUDA(cudaGetDevice(&dev));
     MCEIK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     const long long ntasks = 8LL * a.nbricks * a.nfields_active;
-    const int grid = (int)std::min<long long>((ntasks + kWarps - 1) / kWarps, nsm);
-    sweep_bricks16_kernel<<<grid, kWarps * 32, smem, st>>>(a);
+    if (a.publisher) {
+        MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<long long>((ntasks + kWarps - 2) / (kWarps - 1), nsm);
+        sweep_bricks16_kernel<true><<<grid, kWarps * 32, smem, st>>>(a);
+    } else {
+        MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)std::min<long long>((ntasks + kWarps - 1) / kWarps, nsm);
+        sweep_bricks16_kernel<false><<<grid, kWarps * 32, smem, st>>>(a);
+    }
     MCEIK_LAUNCH_CHECK();
 }
 

@@ -80,6 +80,34 @@ def test_batched_fields_two_models(gpu_ctx, algo):
     assert sol.node_updates == int(n * 8 * its.sum())
 
 
+@pytest.mark.parametrize("publisher", ["0", "1"])
+def test_both_publication_flavours_of_the_brick_kernel(gpu_ctx, publisher):
+    """18 fields (more than the 16 up to which the publisher-warp flavour is the default) with either flavour
+    forced: bit-equal to the oracle, so both launch paths of sweep_bricks16_kernel are parity-tested."""
+    import os
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 40, 24, 300, 200.0
+    n = nx * ny * nz
+    slow = np.stack([cases.checkerboard_slowness(nx, ny, nz, cell=8), cases.random_slowness(n, 21)])
+    nf = 18
+    fmodel = (np.arange(nf) % 2).astype(np.int32)
+    xs, ys, zs = cases.interior_sources(nf, nx, ny, nz, h, seed=4)
+    ts = np.zeros(nf)
+    ref, its = _oracle_fields(nx, ny, nz, h, slow, fmodel[:6], xs[:6], ys[:6], zs[:6], ts[:6], 1e-6, 20)
+    os.environ["MCEIK_FSM_PUBLISHER"] = publisher
+    try:
+        sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
+        u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs)
+    finally:
+        os.environ.pop("MCEIK_FSM_PUBLISHER")
+    assert not ferr.any()
+    assert np.array_equal(iters[:6], its) and np.array_equal(u[:6], ref)
+    # the remaining fields against the other flavour (default for this field count)
+    sol2 = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
+    u2, _, iters2, _ = sol2.solve_host(slow, fmodel, ts, xs, ys, zs)
+    assert np.array_equal(u, u2) and np.array_equal(iters, iters2)
+
+
 def test_pinned_output_is_copied_back_as_fields_converge(gpu_ctx):
     """Page-locked output: fields leave the device as soon as they converge (different iterations per field),
     fields stopped by maxit or refused by the boundary conditions at the end; same bits as the pageable path."""
