@@ -677,67 +677,6 @@ int mceik_locate_batched_dev(mceik_ctx *ctx, int job, int nevents, int nobs_tota
     });
 }
 
-namespace {
-// Ragged catalogues on the fast kernel.  locate_uniform_kernel needs the 8 events of a block to use the same table
-// in every pick slot (unused picks are wildcards).  A block whose events list their used picks in strictly
-// increasing table order is re-laid out over the union of its tables: every event gets one slot per table of the
-// union, "unused" (-1) where it has no pick.  Each event's used picks keep their own order, and unused picks never
-// touch an accumulator, so the results are the same bits.  Other blocks are copied unchanged (general kernel).
-constexpr int kMaxAlignedPicks = 640;  // shared memory of the fast kernel: 260 B per slot
-void align_event_blocks(int nevents, const int *optr, const int *tid, const double *tobs, const double *var,
-                        std::vector<int> &optr2, std::vector<int> &tid2, std::vector<double> &tobs2,
-                        std::vector<double> &var2) {
-    const int EB = gs::kEventsPerBlock;
-    optr2.assign(1, 0);
-    tid2.clear(); tobs2.clear(); var2.clear();
-    std::vector<int> uni;
-    for (int e0 = 0; e0 < nevents; e0 += EB) {
-        const int e1 = std::min(e0 + EB, nevents);
-        int maxp = 0;
-        for (int e = e0; e < e1; ++e) maxp = std::max(maxp, optr[e + 1] - optr[e]);
-        bool uniform = true, sorted = true;
-        for (int j = 0; j < maxp && uniform; ++j) {
-            int id = -1;
-            for (int e = e0; e < e1; ++e)
-                if (j < optr[e + 1] - optr[e]) {
-                    const int t = tid[optr[e] + j];
-                    if (t >= 0) { if (id < 0) id = t; else if (id != t) uniform = false; }
-                }
-        }
-        uni.clear();
-        if (!uniform) {
-            for (int e = e0; e < e1 && sorted; ++e) {
-                int last = -1;
-                for (int p = optr[e]; p < optr[e + 1]; ++p) {
-                    if (tid[p] < 0) continue;
-                    if (tid[p] <= last) { sorted = false; break; }
-                    last = tid[p];
-                    uni.push_back(tid[p]);
-                }
-            }
-            std::sort(uni.begin(), uni.end());
-            uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
-        }
-        if (uniform || !sorted || (int)uni.size() > kMaxAlignedPicks) {
-            for (int e = e0; e < e1; ++e) {
-                for (int p = optr[e]; p < optr[e + 1]; ++p) { tid2.push_back(tid[p]); tobs2.push_back(tobs[p]); var2.push_back(var[p]); }
-                optr2.push_back((int)tid2.size());
-            }
-            continue;
-        }
-        for (int e = e0; e < e1; ++e) {
-            int p = optr[e];
-            for (int u : uni) {
-                while (p < optr[e + 1] && tid[p] < 0) ++p;
-                if (p < optr[e + 1] && tid[p] == u) { tid2.push_back(u); tobs2.push_back(tobs[p]); var2.push_back(var[p]); ++p; }
-                else { tid2.push_back(-1); tobs2.push_back(0.0); var2.push_back(1.0); }
-            }
-            optr2.push_back((int)tid2.size());
-        }
-    }
-}
-}  // namespace
-
 static int locate_host_arrays(mceik_ctx *ctx, int job, int nevents, const std::vector<int> &optr, int np, int maxp,
                               const int *table_id, const double *tobs_cor, const double *varobs, const double *tori, int *iopt,
                               double *t0opt, double *objopt);
@@ -766,7 +705,7 @@ int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *o
         std::vector<int> optr2, tid2;
         std::vector<double> tobs2, var2;
         if (np > 0 && !getenv("MCEIK_LOCATE_NO_ALIGN")) {
-            align_event_blocks(nevents, optr.data(), table_id + obs_ptr[0], tobs_cor + obs_ptr[0], varobs + obs_ptr[0], optr2, tid2,
+            host::align_event_blocks(gs::kEventsPerBlock, nevents, optr.data(), table_id + obs_ptr[0], tobs_cor + obs_ptr[0], varobs + obs_ptr[0], optr2, tid2,
                                tobs2, var2);
             if (tid2.size() != (size_t)np || optr2 != optr) {  // some block was re-laid out: continue with the aligned picks
                 optr.swap(optr2);

@@ -10,3 +10,15 @@ extern "C" int shim_bc_records(int nx, int ny, int nz, double h, double x0, doub
     for (size_t i = 0; i < r.size() && (int)i < cap; ++i) { node[i] = r[i].node; d[i] = r[i].d; t[i] = r[i].ts; colloc[i] = r[i].collocated; }
     return (int)r.size();
 }
+
+// align_event_blocks: returns the number of picks after alignment; arrays sized by the caller (cap picks)
+extern "C" int shim_align_event_blocks(int eb, int nevents, const int *optr, const int *tid, const double *tobs, const double *var,
+                                       int cap, int *optr2, int *tid2, double *tobs2, double *var2) {
+    std::vector<int> o, t;
+    std::vector<double> a, b;
+    mceik::host::align_event_blocks(eb, nevents, optr, tid, tobs, var, o, t, a, b);
+    if ((int)t.size() > cap) return -1;
+    for (int e = 0; e <= nevents; ++e) optr2[e] = o[e];
+    for (size_t i = 0; i < t.size(); ++i) { tid2[i] = t[i]; tobs2[i] = a[i]; var2[i] = b[i]; }
+    return (int)t.size();
+}

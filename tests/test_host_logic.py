@@ -92,3 +92,58 @@ def test_tile_order_equals_hyperplane_order(tmp_path, shape):
                            f"-Wl,-rpath,{O.ORACLE_DIR}"])
     out = subprocess.run([str(exe)] + [str(s) for s in shape], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("MATCH"), out.stdout
+
+
+def _align(shim, eb, optr, tid, tobs, var):
+    optr, tid = np.ascontiguousarray(optr, np.int32), np.ascontiguousarray(tid, np.int32)
+    tobs, var = np.ascontiguousarray(tobs, np.float64), np.ascontiguousarray(var, np.float64)
+    ne = optr.size - 1
+    cap = max(1, 8 * 8 * max(1, tid.size))
+    o2, t2 = np.zeros(ne + 1, np.int32), np.zeros(cap, np.int32)
+    a2, b2 = np.zeros(cap), np.zeros(cap)
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    n = shim.shim_align_event_blocks(eb, ne, p(optr, C.c_int), p(tid, C.c_int), p(tobs, C.c_double), p(var, C.c_double), cap,
+                                     p(o2, C.c_int), p(t2, C.c_int), p(a2, C.c_double), p(b2, C.c_double))
+    assert n >= 0
+    return o2, t2[:n], a2[:n], b2[:n]
+
+
+def test_align_event_blocks(shim):
+    """Ragged pick lists are re-laid out per block of events over the union of their tables (host_logic.hpp):
+    every event keeps its used picks, in its own order; padding picks are unused (-1); a block that is already
+    uniform, or that holds an event not in increasing table order, is copied unchanged."""
+    rng = np.random.default_rng(1)
+    eb, ntab = 4, 12
+    optr, tid, tobs, var = [0], [], [], []
+    lists = []
+    for e in range(11):
+        k = 0 if e == 2 else int(rng.integers(1, ntab + 1))
+        ids = np.sort(rng.permutation(ntab)[:k])
+        if e in (4, 5, 6, 7):                    # block 1 is uniform already (same tables in every slot, one masked pick)
+            ids = np.array([1, 3, 8])
+        if e == 9:                               # block 2 holds an event in decreasing order -> untouched
+            ids = ids[::-1]
+        used = [int(t) if rng.random() > 0.2 else -1 for t in ids]
+        lists.append([(u, float(100 * e + j), 0.25 + j) for j, u in enumerate(used)])
+        for u, a, b in lists[-1]:
+            tid.append(u); tobs.append(a); var.append(b)
+        optr.append(len(tid))
+    o2, t2, a2, b2 = _align(shim, eb, optr, tid, tobs, var)
+    for e in range(11):
+        got = [(int(t2[p]), a2[p], b2[p]) for p in range(o2[e], o2[e + 1])]
+        want_used = [x for x in lists[e] if x[0] >= 0]
+        assert [x for x in got if x[0] >= 0] == want_used            # used picks: same values, same order
+    for b0 in (0, 4, 8):
+        blk = range(b0, min(b0 + eb, 11))
+        if b0 == 0:                              # aligned: same length, same table (or unused) in every slot
+            lens = {o2[e + 1] - o2[e] for e in blk}
+            assert len(lens) == 1
+            for j in range(lens.pop()):
+                ids = {int(t2[o2[e] + j]) for e in blk} - {-1}
+                assert len(ids) <= 1
+            slots = [max(int(t2[o2[e] + j]) for e in blk) for j in range(o2[1] - o2[0])]
+            assert slots == sorted(slots) and -1 not in slots   # the union, in increasing table order
+        else:                                    # copied unchanged
+            for e in blk:
+                got = [(int(t2[p]), a2[p], b2[p]) for p in range(o2[e], o2[e + 1])]
+                assert got == lists[e]
