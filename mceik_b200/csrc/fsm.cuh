@@ -99,6 +99,36 @@ struct BrickArgs {
     int debug;                    // bottleneck experiments only (MCEIK_FSM_DEBUG): 1 no solver, 2 no stores, 4 no loads
 };
 void launch_iteration_bricks(const BrickArgs &a, cudaStream_t st);
+
+// Ticket of the bricks16 queue -> (sweep, brick level, index of the brick in its level, index into `active`).
+// vptr[V] = tickets before virtual level V (built by host::build_ticket_table); shared by the kernel and the CPU test.
+struct TicketTask {
+    int sweep, level, bidx, fidx;
+};
+__host__ __device__ inline TicketTask decode_ticket(long long t, const long long *vptr, const int *blevel_ptr, int nblevels,
+                                                    int stagger, int nf0, int nf1) {
+    const int nvl = 8 * nblevels + stagger;
+    int lo = 0, hi = nvl;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (vptr[mid] <= t) lo = mid; else hi = mid;
+    }
+    long long r = t - vptr[lo];
+    int vl = lo, gnf = nf0, gofs = 0;
+    if (lo < 8 * nblevels) {
+        const int l0 = lo % nblevels;
+        const long long cnt0 = (long long)nf0 * (blevel_ptr[l0 + 1] - blevel_ptr[l0]);
+        if (r >= cnt0) { r -= cnt0; vl = lo - stagger; gnf = nf1; gofs = nf0; }
+    } else {
+        vl = lo - stagger; gnf = nf1; gofs = nf0;
+    }
+    TicketTask k;
+    k.sweep = vl / nblevels;
+    k.level = vl - k.sweep * nblevels;
+    k.bidx = (int)(r / gnf);
+    k.fidx = gofs + (int)(r - (long long)k.bidx * gnf);
+    return k;
+}
 // 16-byte-pair variant (fsm_bricks16.cu): requires nx % 8 == 0 and by == 8
 void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st);
 

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
     const size_t nxy = (size_t)nx * ny, N = nxy * nz;
     const int nf = a.nfields_active;
     const long long ntasks = 8LL * a.nbricks * nf;
-    const int nl = a.nblevels, nvl = 8 * nl + a.stagger, nf0 = a.nf0, nf1 = nf - a.nf0;
+    const int nl = a.nblevels, nf0 = a.nf0, nf1 = nf - a.nf0;
     // compute map: lane -> sweep column li and rows j0, j0 + 1
     const int li = lane >> 2, j0 = kNC * (lane & 3);
     const int ig = xgroup(li);
@@ -159,24 +159,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         const long long t_start = a.stats ? clock64() : 0;
 
         // ---- ticket -> virtual level -> (group, sweep, brick level, brick, field)
-        int lo = 0, hi = nvl;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(a.vptr + mid) <= t) lo = mid; else hi = mid;
-        }
-        long long r = t - __ldg(a.vptr + lo);
-        int vl = lo, gnf = nf0, gofs = 0;
-        if (lo < 8 * nl) {
-            const int l0 = lo % nl;
-            const long long cnt0 = (long long)nf0 * (__ldg(a.blevel_ptr + l0 + 1) - __ldg(a.blevel_ptr + l0));
-            if (r >= cnt0) { r -= cnt0; vl = lo - a.stagger; gnf = nf1; gofs = nf0; }
-        } else {
-            vl = lo - a.stagger; gnf = nf1; gofs = nf0;
-        }
-        const int s = vl / nl, lev = vl - s * nl;
-        const int bidx = (int)(r / gnf);
-        const int f = __ldg(a.active + gofs + (int)(r - (long long)bidx * gnf));
-        const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + lev) + bidx);
+        const TicketTask task = decode_ticket(t, a.vptr, a.blevel_ptr, nl, a.stagger, nf0, nf1);
+        const int s = task.sweep;
+        const int f = __ldg(a.active + task.fidx);
+        const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + task.level) + task.bidx);
         const bool revx = (s & 1) != 0, revy = (s & 2) != 0, revz = (s & 4) != 0;  // fsm3d.f90:46-53
         int I = packed & 1023, J = (packed >> 10) & 1023, K = packed >> 20;
         if (revx) I = a.nbx - 1 - I;

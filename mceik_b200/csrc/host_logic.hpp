@@ -135,5 +135,22 @@ inline void align_event_blocks(int EB, int nevents, const int *optr, const int *
     }
 }
 
+
+// Ticket table of the bricks16 queue (BrickArgs::vptr): the active fields form two groups, group 1 runs `stagger`
+// brick levels behind group 0; virtual level V holds level V % nblevels of sweep V / nblevels for group 0 and the
+// same of V - stagger for group 1.  vptr[V] = number of tickets before V; vptr.back() = 8 * nbricks * nfields.
+inline std::vector<long long> build_ticket_table(int nblevels, const int *blevel_ptr, int nfields, int nf0, int stagger) {
+    const int nvl = 8 * nblevels + stagger, nf1 = nfields - nf0;
+    std::vector<long long> vptr(nvl + 1, 0);
+    for (int v = 0; v < nvl; ++v) {
+        long long cnt = 0;
+        if (v < 8 * nblevels) cnt += (long long)nf0 * (blevel_ptr[v % nblevels + 1] - blevel_ptr[v % nblevels]);
+        const int v1 = v - stagger;
+        if (nf1 > 0 && v1 >= 0 && v1 < 8 * nblevels) cnt += (long long)nf1 * (blevel_ptr[v1 % nblevels + 1] - blevel_ptr[v1 % nblevels]);
+        vptr[v + 1] = vptr[v] + cnt;
+    }
+    return vptr;
+}
+
 }  // namespace host
 }  // namespace mceik

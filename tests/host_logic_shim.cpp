@@ -22,3 +22,15 @@ extern "C" int shim_align_event_blocks(int eb, int nevents, const int *optr, con
     for (size_t i = 0; i < t.size(); ++i) { tid2[i] = t[i]; tobs2[i] = a[i]; var2[i] = b[i]; }
     return (int)t.size();
 }
+
+// bricks16 ticket queue: table + decode (the decode is the same __host__ __device__ function the kernel calls)
+extern "C" long long shim_ticket_table(int nblevels, const int *blevel_ptr, int nfields, int nf0, int stagger, long long *vptr) {
+    const std::vector<long long> v = mceik::host::build_ticket_table(nblevels, blevel_ptr, nfields, nf0, stagger);
+    for (size_t i = 0; i < v.size(); ++i) vptr[i] = v[i];
+    return v.back();
+}
+extern "C" void shim_decode_ticket(long long t, const long long *vptr, const int *blevel_ptr, int nblevels, int stagger, int nf0,
+                                   int nf1, int *out4) {
+    const mceik::fsm::TicketTask k = mceik::fsm::decode_ticket(t, vptr, blevel_ptr, nblevels, stagger, nf0, nf1);
+    out4[0] = k.sweep; out4[1] = k.level; out4[2] = k.bidx; out4[3] = k.fidx;
+}

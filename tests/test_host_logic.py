@@ -147,3 +147,43 @@ def test_align_event_blocks(shim):
             for e in blk:
                 got = [(int(t2[p]), a2[p], b2[p]) for p in range(o2[e], o2[e + 1])]
                 assert got == lists[e]
+
+
+@pytest.mark.parametrize("nf,nf0,stagger_on", [(5, 3, True), (4, 4, False), (1, 1, False), (13, 7, True)])
+def test_ticket_queue_is_a_valid_order(shim, nf, nf0, stagger_on):
+    """The ticket order of the streaming brick kernel (two field groups, the second `stagger` brick levels behind):
+    every (sweep, brick, field) task appears exactly once, and along the queue each field's tasks never go back
+    in (sweep, level) -- the only order its dependencies need (same field, earlier sweep or lower level)."""
+    nbx, nby, nbz = 3, 4, 2
+    nl = nbx + nby + nbz - 2
+    ptr, order = [0], []
+    for d in range(nl):                      # BrickPlan::build: bricks sorted by I + J + K
+        for K in range(nbz):
+            for J in range(nby):
+                I = d - K - J
+                if 0 <= I < nbx:
+                    order.append((I, J, K))
+        ptr.append(len(order))
+    nbricks = len(order)
+    assert nbricks == nbx * nby * nbz
+    stagger = nl // 2 if stagger_on else 0
+    bl = np.array(ptr, np.int32)
+    vptr = np.zeros(8 * nl + stagger + 1, np.int64)
+    p = lambda a, ty: a.ctypes.data_as(C.POINTER(ty))
+    shim.shim_ticket_table.restype = C.c_longlong
+    total = shim.shim_ticket_table(nl, p(bl, C.c_int), nf, nf0, stagger, p(vptr, C.c_longlong))
+    assert total == 8 * nbricks * nf and np.all(np.diff(vptr) >= 0)
+    seen = set()
+    last = {}
+    out = np.zeros(4, np.int32)
+    for t in range(total):
+        shim.shim_decode_ticket(C.c_longlong(t), p(vptr, C.c_longlong), p(bl, C.c_int), nl, stagger, nf0, nf - nf0, p(out, C.c_int))
+        s, lev, bidx, f = (int(x) for x in out)
+        assert 0 <= s < 8 and 0 <= lev < nl and 0 <= bidx < ptr[lev + 1] - ptr[lev] and 0 <= f < nf
+        key = (s, ptr[lev] + bidx, f)
+        assert key not in seen
+        seen.add(key)
+        pos = s * nl + lev
+        assert pos >= last.get(f, -1)
+        last[f] = pos
+    assert len(seen) == total
