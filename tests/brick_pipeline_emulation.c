@@ -1,0 +1,235 @@
+/*
+ * tests/brick_pipeline_emulation.c -- CPU model of the streaming brick kernel's SCHEDULE
+ * (mceik_b200/csrc/fsm_bricks16.cu), using the oracle's local solver.  Test infrastructure.
+ *
+ * What is modelled, with the kernel's own constants:
+ *   - bricks of 8 x 8 x zc nodes; a brick (one warp) advances in steps; at step l it updates its nodes
+ *     with i + j + k = l (sweep-frame brick coordinates);
+ *   - cell (i,j,k), i in [-1,8], j in [-1,ey], k in [-1,ez], belongs to ring slot
+ *     m = xgroup(i) + (j+1) + (k+1); slot m is LOADED from global memory (halo cells outside the grid
+ *     clamped to the boundary node) when step m - 6 starts -- long before it is used -- and the in-brick
+ *     cells of slot l - 3 are STORED at the end of step l;
+ *   - a brick may load slot m only when its upwind y neighbour has completed m + By + 4 steps and its
+ *     upwind x neighbour m + 6 (the fine-grained dependencies of the kernel), and starts only after its
+ *     upwind z neighbour has finished;
+ *   - bricks that may advance are picked in RANDOM order, so every run explores another interleaving.
+ * It asserts the ring lifetime the kernel relies on (a cell is read in steps [m-4, m+4] and written in
+ * [m-3, m+3], i.e. 11 slots with the two prefetched ones) and that every value read had been loaded.
+ * The result must equal the reference-ordered oracle bit for bit for every interleaving; with a lead
+ * one step shorter (argv) it must not be relied upon -- the test checks that the model notices.
+ *
+ * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead]  -> "MATCH iters=<k> stalls=<n>" or "MISMATCH ..."
+ */
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+double oracle_hamiltonian3d(double a, double b, double c, double f, int *ierr);
+void oracle_eikonal3d_serial_driver(const int *, const int *, const int *, const int *, const int *, const int *,
+                                    const int *, const double *, const double *, const double *, const double *,
+                                    const double *, const double *, const double *, const double *, const double *,
+                                    const double *, double *, int *);
+int oracle_setbcs(int, int, int, int, double, double, double, double, double, double, const double *, const double *,
+                  const double *, const double *, const double *, unsigned char *, double *);
+int oracle_last_iterations(void);
+
+#define BX 8
+#define BY 8
+#define PREFETCH 2
+#define AHEAD (4 + PREFETCH)          /* slot l + AHEAD is loaded when step l starts */
+#define DONE_ALL 1000000
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+static int xgroup(int i) { return (i + 4) >> 2; }
+
+typedef struct {
+    int I, J, K;            /* global brick coordinates */
+    int x_lo, y_lo, y_hi, z_lo, z_hi, ey, ez;
+    int progress;           /* steps completed, DONE_ALL when finished */
+    int loaded;             /* highest slot loaded so far, -1 before the start */
+    double *L;              /* (BX+2) x (BY+2) x (ez+2) local cells */
+    unsigned char *have;    /* cell has been loaded */
+} brick_t;
+
+static int nx, ny, nz, zc, nbx, nby, nbz;
+static long nxy;
+static double h;
+static const double *slow;
+static const unsigned char *lisbc;
+static double *u;
+static int revx, revy, revz, lead_x, lead_y;
+static long ring_violations, unloaded_reads;
+
+#define LIDX(b, i, j, k) ((((long)(k) + 1) * (BY + 2) + ((j) + 1)) * (BX + 2) + ((i) + 1))
+
+static long gnode(const brick_t *b, int i, int j, int k)
+{ /* sweep-frame brick cell -> clamped global node */
+    int gx = revx ? b->x_lo + BX - 1 - i : b->x_lo + i;
+    int gy = revy ? b->y_hi - j : b->y_lo + j;
+    int gz = revz ? b->z_hi - k : b->z_lo + k;
+    gx = imin(imax(gx, 0), nx - 1); gy = imin(imax(gy, 0), ny - 1); gz = imin(imax(gz, 0), nz - 1);
+    return (long)gz * nxy + (long)gy * nx + gx;
+}
+
+static brick_t *brick_at(brick_t *bk, int I, int J, int K)
+{
+    if (I < 0 || I >= nbx || J < 0 || J >= nby || K < 0 || K >= nbz) return NULL;
+    return bk + ((long)K * nby + J) * nbx + I;
+}
+
+static int may_load(brick_t *bk, const brick_t *b, int m)
+{
+    const brick_t *ux = brick_at(bk, b->I + (revx ? 1 : -1), b->J, b->K);
+    const brick_t *uy = brick_at(bk, b->I, b->J + (revy ? 1 : -1), b->K);
+    if (ux && ux->progress < m + lead_x) return 0;
+    if (uy && uy->progress < m + lead_y) return 0;
+    return 1;
+}
+
+static void load_slot(brick_t *b, int m)
+{
+    for (int k = -1; k <= b->ez; k++)
+        for (int j = -1; j <= b->ey; j++)
+            for (int i = -1; i <= BX; i++)
+                if (xgroup(i) + (j + 1) + (k + 1) == m) {
+                    b->L[LIDX(b, i, j, k)] = u[gnode(b, i, j, k)];
+                    b->have[LIDX(b, i, j, k)] = 1;
+                }
+    b->loaded = m;
+}
+
+static double rd(brick_t *b, int i, int j, int k, int l)
+{
+    const int m = xgroup(i) + (j + 1) + (k + 1);
+    if (l < m - 4 || l > m + 4) ring_violations++;
+    if (!b->have[LIDX(b, i, j, k)] || m > l + 4) unloaded_reads++;
+    return b->L[LIDX(b, i, j, k)];
+}
+
+static void step(brick_t *b)
+{
+    const int l = b->progress;
+    for (int k = 0; k < b->ez; k++)
+        for (int j = 0; j < b->ey; j++) {
+            const int i = l - j - k;
+            if (i < 0 || i >= BX) continue;
+            const long g = gnode(b, i, j, k);
+            if (lisbc[g]) continue;
+            const int m = xgroup(i) + (j + 1) + (k + 1);
+            if (l < m - 3 || l > m + 3) ring_violations++;
+            const double self = rd(b, i, j, k, l);
+            const double xm = rd(b, i - 1, j, k, l), xp = rd(b, i + 1, j, k, l);
+            const double ym = rd(b, i, j - 1, k, l), yp = rd(b, i, j + 1, k, l);
+            const double zm = rd(b, i, j, k - 1, l), zp = rd(b, i, j, k + 1, l);
+            const double ux = xm < xp ? xm : xp, uy = ym < yp ? ym : yp, uz = zm < zp ? zm : zp;
+            int ierr;
+            const double ubar = oracle_hamiltonian3d(ux, uy, uz, slow[g] * h, &ierr);
+            if (ubar < self) b->L[LIDX(b, i, j, k)] = ubar;
+        }
+    /* write back the in-brick cells of slot l - 3 */
+    for (int k = 0; k < b->ez; k++)
+        for (int j = 0; j < b->ey; j++)
+            for (int i = 0; i < BX; i++)
+                if (xgroup(i) + (j + 1) + (k + 1) == l - 3) u[gnode(b, i, j, k)] = b->L[LIDX(b, i, j, k)];
+    b->progress = l + 1;
+}
+
+static long sweep(brick_t *bk, long nb, unsigned *rng)
+{
+    long stalls = 0, left = nb;
+    for (long q = 0; q < nb; q++) {
+        brick_t *b = bk + q;
+        b->progress = 0; b->loaded = -1;
+        memset(b->have, 0, (size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
+    }
+    long idle = 0;
+    while (left > 0) {
+        *rng = *rng * 1664525u + 1013904223u;
+        brick_t *b = bk + (*rng >> 8) % nb;
+        if (b->progress == DONE_ALL) continue;
+        const int nsteps = b->ez + BY + 6;
+        int moved = 0;
+        if (b->loaded < 0) {  /* start: the upwind z neighbour has finished; slots 0 .. AHEAD-1 */
+            const brick_t *uz = brick_at(bk, b->I, b->J, b->K + (revz ? 1 : -1));
+            if ((!uz || uz->progress == DONE_ALL) && may_load(bk, b, AHEAD - 1)) {
+                for (int m = 0; m < AHEAD; m++) load_slot(b, m);
+                moved = 1;
+            }
+        } else if (may_load(bk, b, b->progress + AHEAD)) {
+            load_slot(b, b->progress + AHEAD);
+            step(b);
+            if (b->progress == nsteps) { b->progress = DONE_ALL; left--; }
+            moved = 1;
+        }
+        if (moved) idle = 0;
+        else { stalls++; if (++idle > 200 * nb + 100000) { printf("DEADLOCK\n"); exit(3); } }
+    }
+    return stalls;
+}
+
+int main(int argc, char **argv)
+{
+    nx = argc > 1 ? atoi(argv[1]) : 24; ny = argc > 2 ? atoi(argv[2]) : 20; nz = argc > 3 ? atoi(argv[3]) : 22;
+    zc = argc > 4 ? atoi(argv[4]) : 16;
+    unsigned rng = argc > 5 ? (unsigned)atoi(argv[5]) : 1u;
+    const int dlead = argc > 6 ? atoi(argv[6]) : 0;
+    lead_x = 6 + dlead; lead_y = BY + 4 + dlead;
+    if (nx % BX) { printf("nx must be a multiple of 8\n"); return 2; }
+    nxy = (long)nx * ny;
+    long n = nxy * nz;
+    h = 100.0;
+    double tol = 1e-6, x0 = 0, y0 = 0, z0 = 0;
+    int maxit = 20, nsrc = 2, iverb = 0, ierr;
+    double ts[2] = {0.0, 0.3}, xs[2] = {h * (nx * 0.37), h * (nx * 0.8)}, ys[2] = {h * (ny * 0.61), h * 2.0},
+           zs[2] = {h * (nz * 0.45), h * (nz - 2.5)};
+    double *sl = malloc(sizeof(double) * n), *uref = malloc(sizeof(double) * n), *u0 = malloc(sizeof(double) * n);
+    unsigned char *bc = malloc(n);
+    u = malloc(sizeof(double) * n);
+    srand(7);
+    for (long i = 0; i < n; i++) sl[i] = 1.0 / (3000.0 + 2500.0 * (rand() / (double)RAND_MAX));
+    slow = sl; lisbc = bc;
+    int job = 1;
+#define DRV() oracle_eikonal3d_serial_driver(&job, &iverb, &maxit, &nsrc, &nx, &ny, &nz, &tol, &h, &x0, &y0, &z0, ts, xs, ys, zs, sl, uref, &ierr)
+    DRV(); job = 2; DRV();
+    if (ierr) { printf("oracle ierr\n"); return 2; }
+    const int ref_iters = oracle_last_iterations();
+    job = 3; DRV();
+    if (oracle_setbcs(nx, ny, nz, nsrc, h, h, h, x0, y0, z0, ts, xs, ys, zs, sl, bc, u)) return 2;
+
+    nbx = nx / BX; nby = (ny + BY - 1) / BY; nbz = (nz + zc - 1) / zc;
+    const long nb = (long)nbx * nby * nbz;
+    brick_t *bk = calloc(nb, sizeof(brick_t));
+    for (int K = 0; K < nbz; K++) for (int J = 0; J < nby; J++) for (int I = 0; I < nbx; I++) {
+        brick_t *b = brick_at(bk, I, J, K);
+        b->I = I; b->J = J; b->K = K;
+        b->x_lo = I * BX; b->y_lo = J * BY; b->y_hi = imin(b->y_lo + BY, ny) - 1;
+        b->z_lo = K * zc; b->z_hi = imin(b->z_lo + zc, nz) - 1;
+        b->ey = b->y_hi - b->y_lo + 1; b->ez = b->z_hi - b->z_lo + 1;
+        b->L = malloc(sizeof(double) * (BX + 2) * (BY + 2) * (b->ez + 2));
+        b->have = malloc((size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
+    }
+    long stalls = 0;
+    int it;
+    for (it = 1; it <= maxit; it++) {
+        memcpy(u0, u, sizeof(double) * n);
+        for (int s = 0; s < 8; s++) {
+            revx = s & 1; revy = (s >> 1) & 1; revz = (s >> 2) & 1;   /* fsm3d.f90:46-53 */
+            stalls += sweep(bk, nb, &rng);
+        }
+        long lconv = 0;
+        for (long i = 0; i < n; i++) if (fabs(u0[i] - u[i]) < tol) lconv++;
+        if (lconv == n) break;
+    }
+    if (it > maxit) it = maxit;
+    long bad = 0;
+    for (long i = 0; i < n; i++) if (u[i] != uref[i]) bad++;
+    if (bad || it != ref_iters || ring_violations || unloaded_reads)
+        printf("MISMATCH nodes=%ld iters=%d ref_iters=%d ring_violations=%ld unloaded_reads=%ld\n", bad, it, ref_iters,
+               ring_violations, unloaded_reads);
+    else
+        printf("MATCH iters=%d stalls=%ld\n", it, stalls);
+    return (bad || it != ref_iters || ring_violations || unloaded_reads) ? 1 : 0;
+}

@@ -187,3 +187,29 @@ def test_ticket_queue_is_a_valid_order(shim, nf, nf0, stagger_on):
         assert pos >= last.get(f, -1)
         last[f] = pos
     assert len(seen) == total
+
+
+@pytest.fixture(scope="module")
+def brick_emu(tmp_path_factory):
+    O.build()
+    exe = tmp_path_factory.mktemp("brick_emu") / "brick_emu"
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-ffp-contract=off", "-o", str(exe),
+                           os.path.join(ROOT, "tests", "brick_pipeline_emulation.c"), "-L", O.ORACLE_DIR, "-loracle", "-lm",
+                           f"-Wl,-rpath,{O.ORACLE_DIR}"])
+    return str(exe)
+
+
+@pytest.mark.parametrize("args", [(24, 20, 22, 16, 1), (24, 20, 22, 16, 2), (16, 9, 40, 256, 3), (32, 24, 18, 8, 4),
+                                  (8, 8, 30, 16, 5), (40, 17, 33, 32, 6)])
+def test_brick_pipeline_schedule_reproduces_the_reference_order(brick_emu, args):
+    """tests/brick_pipeline_emulation.c: the streaming brick schedule of fsm_bricks16.cu (ring slots loaded 6 steps
+    ahead, write-back 3 steps behind, upwind y neighbour By + 4 and x neighbour 6 steps ahead, random interleaving of
+    the bricks) gives the reference-ordered oracle bit for bit and stays inside the 11-slot ring."""
+    out = subprocess.run([brick_emu] + [str(a) for a in args], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("MATCH"), out.stdout
+
+
+def test_brick_pipeline_leads_are_tight(brick_emu):
+    """One step less lead on the upwind neighbours and the same model reads halo values too early."""
+    out = subprocess.run([brick_emu, "24", "20", "22", "16", "1", "-1"], capture_output=True, text=True)
+    assert out.returncode == 1 and out.stdout.startswith("MISMATCH"), out.stdout
