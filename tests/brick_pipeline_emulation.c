@@ -12,6 +12,9 @@
  *   - a brick may load slot m only when its upwind y neighbour has completed m + By + 4 steps and its
  *     upwind x neighbour m + 6 (the fine-grained dependencies of the kernel), and starts only after its
  *     upwind z neighbour has finished;
+ *   - the 8 sweeps of an iteration OVERLAP as in the kernel: a brick starts sweep s as soon as it and its six face
+ *     neighbours have completed sweep s - 1 (and its upwind z neighbour sweep s), while other bricks are still in
+ *     earlier sweeps; only the iterations are separated (one kernel launch each);
  *   - bricks that may advance are picked in RANDOM order, so every run explores another interleaving.
  * It asserts the ring lifetime the kernel relies on (a cell is read in steps [m-4, m+4] and written in
  * [m-3, m+3], i.e. 11 slots with the two prefetched ones) and that every value read had been loaded.
@@ -39,7 +42,6 @@ int oracle_last_iterations(void);
 #define BY 8
 #define PREFETCH 2
 #define AHEAD (4 + PREFETCH)          /* slot l + AHEAD is loaded when step l starts */
-#define DONE_ALL 1000000
 
 static int imin(int a, int b) { return a < b ? a : b; }
 static int imax(int a, int b) { return a > b ? a : b; }
@@ -48,7 +50,8 @@ static int xgroup(int i) { return (i + 4) >> 2; }
 typedef struct {
     int I, J, K;            /* global brick coordinates */
     int x_lo, y_lo, y_hi, z_lo, z_hi, ey, ez;
-    int progress;           /* steps completed, DONE_ALL when finished */
+    int sweep;              /* sweep being worked on (0..7), 8 when the iteration is finished */
+    int progress;           /* steps completed in that sweep */
     int loaded;             /* highest slot loaded so far, -1 before the start */
     double *L;              /* (BX+2) x (BY+2) x (ez+2) local cells */
     unsigned char *have;    /* cell has been loaded */
@@ -60,16 +63,20 @@ static double h;
 static const double *slow;
 static const unsigned char *lisbc;
 static double *u;
-static int revx, revy, revz, lead_x, lead_y;
+static int lead_x, lead_y;
+#define REVX(s) ((s) & 1)
+#define REVY(s) (((s) >> 1) & 1)
+#define REVZ(s) (((s) >> 2) & 1)   /* fsm3d.f90:46-53 */
 static long ring_violations, unloaded_reads;
 
 #define LIDX(b, i, j, k) ((((long)(k) + 1) * (BY + 2) + ((j) + 1)) * (BX + 2) + ((i) + 1))
 
 static long gnode(const brick_t *b, int i, int j, int k)
 { /* sweep-frame brick cell -> clamped global node */
-    int gx = revx ? b->x_lo + BX - 1 - i : b->x_lo + i;
-    int gy = revy ? b->y_hi - j : b->y_lo + j;
-    int gz = revz ? b->z_hi - k : b->z_lo + k;
+    const int sw = b->sweep;
+    int gx = REVX(sw) ? b->x_lo + BX - 1 - i : b->x_lo + i;
+    int gy = REVY(sw) ? b->y_hi - j : b->y_lo + j;
+    int gz = REVZ(sw) ? b->z_hi - k : b->z_lo + k;
     gx = imin(imax(gx, 0), nx - 1); gy = imin(imax(gy, 0), ny - 1); gz = imin(imax(gz, 0), nz - 1);
     return (long)gz * nxy + (long)gy * nx + gx;
 }
@@ -80,12 +87,30 @@ static brick_t *brick_at(brick_t *bk, int I, int J, int K)
     return bk + ((long)K * nby + J) * nbx + I;
 }
 
+/* progress word of the kernel: (sweep << 12) + steps completed in it; a finished sweep counts as (sweep + 1) << 12 */
+static int word(const brick_t *b) { return (b->sweep << 12) + b->progress; }
+
 static int may_load(brick_t *bk, const brick_t *b, int m)
 {
-    const brick_t *ux = brick_at(bk, b->I + (revx ? 1 : -1), b->J, b->K);
-    const brick_t *uy = brick_at(bk, b->I, b->J + (revy ? 1 : -1), b->K);
-    if (ux && ux->progress < m + lead_x) return 0;
-    if (uy && uy->progress < m + lead_y) return 0;
+    const int sw = b->sweep;
+    const brick_t *ux = brick_at(bk, b->I + (REVX(sw) ? 1 : -1), b->J, b->K);
+    const brick_t *uy = brick_at(bk, b->I, b->J + (REVY(sw) ? 1 : -1), b->K);
+    if (ux && word(ux) < (sw << 12) + m + lead_x) return 0;
+    if (uy && word(uy) < (sw << 12) + m + lead_y) return 0;
+    return 1;
+}
+
+static int may_start(brick_t *bk, const brick_t *b)
+{ /* the brick and its six face neighbours have completed the previous sweep, the upwind z neighbour this one */
+    const int sw = b->sweep;
+    static const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    for (int q = 0; q < 6; q++) {
+        const brick_t *nb = brick_at(bk, b->I + d[q][0], b->J + d[q][1], b->K + d[q][2]);
+        if (!nb) continue;
+        int need = sw << 12;
+        if (d[q][2] != 0 && d[q][2] == (REVZ(sw) ? 1 : -1)) need = (sw + 1) << 12;
+        if (word(nb) < need) return 0;
+    }
     return 1;
 }
 
@@ -137,31 +162,29 @@ static void step(brick_t *b)
     b->progress = l + 1;
 }
 
-static long sweep(brick_t *bk, long nb, unsigned *rng)
+static long iteration(brick_t *bk, long nb, unsigned *rng)
 {
-    long stalls = 0, left = nb;
-    for (long q = 0; q < nb; q++) {
-        brick_t *b = bk + q;
-        b->progress = 0; b->loaded = -1;
-        memset(b->have, 0, (size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
-    }
-    long idle = 0;
+    long stalls = 0, left = nb, idle = 0;
+    for (long q = 0; q < nb; q++) { bk[q].sweep = 0; bk[q].progress = 0; bk[q].loaded = -1; }
     while (left > 0) {
         *rng = *rng * 1664525u + 1013904223u;
         brick_t *b = bk + (*rng >> 8) % nb;
-        if (b->progress == DONE_ALL) continue;
+        if (b->sweep == 8) continue;
         const int nsteps = b->ez + BY + 6;
         int moved = 0;
-        if (b->loaded < 0) {  /* start: the upwind z neighbour has finished; slots 0 .. AHEAD-1 */
-            const brick_t *uz = brick_at(bk, b->I, b->J, b->K + (revz ? 1 : -1));
-            if ((!uz || uz->progress == DONE_ALL) && may_load(bk, b, AHEAD - 1)) {
+        if (b->loaded < 0) {  /* start of a sweep: slots 0 .. AHEAD-1 */
+            if (may_start(bk, b) && may_load(bk, b, AHEAD - 1)) {
+                memset(b->have, 0, (size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
                 for (int m = 0; m < AHEAD; m++) load_slot(b, m);
                 moved = 1;
             }
         } else if (may_load(bk, b, b->progress + AHEAD)) {
             load_slot(b, b->progress + AHEAD);
             step(b);
-            if (b->progress == nsteps) { b->progress = DONE_ALL; left--; }
+            if (b->progress == nsteps) {  /* (sweep + 1) << 12 in the kernel's progress word */
+                b->sweep++; b->progress = 0; b->loaded = -1;
+                if (b->sweep == 8) left--;
+            }
             moved = 1;
         }
         if (moved) idle = 0;
@@ -215,10 +238,7 @@ int main(int argc, char **argv)
     int it;
     for (it = 1; it <= maxit; it++) {
         memcpy(u0, u, sizeof(double) * n);
-        for (int s = 0; s < 8; s++) {
-            revx = s & 1; revy = (s >> 1) & 1; revz = (s >> 2) & 1;   /* fsm3d.f90:46-53 */
-            stalls += sweep(bk, nb, &rng);
-        }
+        stalls += iteration(bk, nb, &rng);
         long lconv = 0;
         for (long i = 0; i < n; i++) if (fabs(u0[i] - u[i]) < tol) lconv++;
         if (lconv == n) break;
