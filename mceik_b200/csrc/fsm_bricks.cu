@@ -13,7 +13,7 @@
 //     time cells + 8x8 slowness cells each) filled by cp.async two slots ahead in 32-byte sectors,
 //     updated in place, and written back as soon as a slot is final.  Nothing but the ring is ever
 //     staged, so loads, the 64 Godunov updates per step and stores overlap continuously, and
-//     15 warps (one brick each) are resident per SM.
+//     12 warps (one brick each) are resident per SM.
 //   * Bricks form the same DAG as tiles; a persistent grid of independent warps pulls tickets in a
 //     topological order and spins on per-(field, brick) completion counters.
 #include <algorithm>

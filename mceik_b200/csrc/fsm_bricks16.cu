@@ -12,6 +12,14 @@
 //     order; the sweep direction only decides which of the two x-neighbours is "upwind" and which
 //     slot it lives in.  Rows (y) and planes (z) stay in sweep order.
 //
+//   * steps in which every transfer, update and store touches in-brick nodes run in whole publication chunks
+//     with all global addresses formed as (per-task byte base) + (one running plane offset);
+//   * a warp waits for its upwind x neighbour By - 2 steps less than for its upwind y neighbour, remembers the
+//     progress it has already observed and looks one chunk ahead;
+//   * tickets interleave two groups of fields half a sweep apart (decode_ticket, fsm.cuh);
+//   * with few active fields the kernel runs in its publisher flavour (template parameter): the last warp of
+//     the CTA executes the gpu-scope fences and progress stores for the others.
+//
 // nx % 8 == 0 makes every brick full in x and every pair 16-byte aligned; other grids use
 // sweep_bricks_kernel.  Bricks at the grid's x faces fetch their clamped halo column (a copy of the
 // boundary column itself, fsm3d.f90:495-499) with an 8-byte cp.async.
