@@ -21,7 +21,12 @@
  * The result must equal the reference-ordered oracle bit for bit for every interleaving; with a lead
  * one step shorter (argv) it must not be relied upon -- the test checks that the model notices.
  *
- * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead]  -> "MATCH iters=<k> stalls=<n>" or "MISMATCH ..."
+ * Optional study (argv[7] = 1), not part of the kernel yet: skip a brick's sweep when it and its six face neighbours
+ * changed nothing in the previous sweep and its upwind neighbours have finished the current one without a change
+ * (an update whose inputs did not change is idempotent).  The model reports how many brick sweeps that skips and
+ * must still give the oracle's bits.
+ *
+ * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead [skip]]  -> "MATCH iters=<k> stalls=<n> ..." or "MISMATCH ..."
  */
 #include <float.h>
 #include <math.h>
@@ -53,6 +58,8 @@ typedef struct {
     int sweep;              /* sweep being worked on (0..7), 8 when the iteration is finished */
     int progress;           /* steps completed in that sweep */
     int loaded;             /* highest slot loaded so far, -1 before the start */
+    long last_changed;      /* global sweep (8 * iteration + sweep) in which the brick last changed a node */
+    int changed;            /* ... in the sweep being worked on */
     double *L;              /* (BX+2) x (BY+2) x (ez+2) local cells */
     unsigned char *have;    /* cell has been loaded */
 } brick_t;
@@ -67,7 +74,8 @@ static int lead_x, lead_y;
 #define REVX(s) ((s) & 1)
 #define REVY(s) (((s) >> 1) & 1)
 #define REVZ(s) (((s) >> 2) & 1)   /* fsm3d.f90:46-53 */
-static long ring_violations, unloaded_reads;
+static long ring_violations, unloaded_reads, gsweep0, skipped, tasks;
+static int skip_mode;
 
 #define LIDX(b, i, j, k) ((((long)(k) + 1) * (BY + 2) + ((j) + 1)) * (BX + 2) + ((i) + 1))
 
@@ -114,6 +122,24 @@ static int may_start(brick_t *bk, const brick_t *b)
     return 1;
 }
 
+/* skip study: 1 = skip this sweep, 0 = run it, -1 = cannot tell yet (an upwind neighbour is still sweeping) */
+static int may_skip(brick_t *bk, const brick_t *b)
+{
+    const int sw = b->sweep;
+    const long G = gsweep0 + sw;
+    static const int d[7][3] = {{0, 0, 0}, {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    for (int q = 0; q < 7; q++) {
+        const brick_t *nb = brick_at(bk, b->I + d[q][0], b->J + d[q][1], b->K + d[q][2]);
+        if (nb && nb->last_changed >= G - 1) return 0;   /* changed in the previous sweep, or already in this one */
+    }
+    const int up[3][3] = {{REVX(sw) ? 1 : -1, 0, 0}, {0, REVY(sw) ? 1 : -1, 0}, {0, 0, REVZ(sw) ? 1 : -1}};
+    for (int q = 0; q < 3; q++) {
+        const brick_t *nb = brick_at(bk, b->I + up[q][0], b->J + up[q][1], b->K + up[q][2]);
+        if (nb && word(nb) < ((sw + 1) << 12)) return -1;
+    }
+    return 1;
+}
+
 static void load_slot(brick_t *b, int m)
 {
     for (int k = -1; k <= b->ez; k++)
@@ -152,7 +178,7 @@ static void step(brick_t *b)
             const double ux = xm < xp ? xm : xp, uy = ym < yp ? ym : yp, uz = zm < zp ? zm : zp;
             int ierr;
             const double ubar = oracle_hamiltonian3d(ux, uy, uz, slow[g] * h, &ierr);
-            if (ubar < self) b->L[LIDX(b, i, j, k)] = ubar;
+            if (ubar < self) { b->L[LIDX(b, i, j, k)] = ubar; b->changed = 1; }
         }
     /* write back the in-brick cells of slot l - 3 */
     for (int k = 0; k < b->ez; k++)
@@ -173,7 +199,13 @@ static long iteration(brick_t *bk, long nb, unsigned *rng)
         const int nsteps = b->ez + BY + 6;
         int moved = 0;
         if (b->loaded < 0) {  /* start of a sweep: slots 0 .. AHEAD-1 */
-            if (may_start(bk, b) && may_load(bk, b, AHEAD - 1)) {
+            const int sk = (skip_mode && may_start(bk, b)) ? may_skip(bk, b) : 0;
+            if (sk == 1) {
+                b->sweep++; skipped++; tasks++;
+                if (b->sweep == 8) left--;
+                moved = 1;
+            } else if (sk == 0 && may_start(bk, b) && may_load(bk, b, AHEAD - 1)) {
+                b->changed = 0;
                 memset(b->have, 0, (size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
                 for (int m = 0; m < AHEAD; m++) load_slot(b, m);
                 moved = 1;
@@ -182,7 +214,8 @@ static long iteration(brick_t *bk, long nb, unsigned *rng)
             load_slot(b, b->progress + AHEAD);
             step(b);
             if (b->progress == nsteps) {  /* (sweep + 1) << 12 in the kernel's progress word */
-                b->sweep++; b->progress = 0; b->loaded = -1;
+                if (b->changed) b->last_changed = gsweep0 + b->sweep;
+                b->sweep++; b->progress = 0; b->loaded = -1; tasks++;
                 if (b->sweep == 8) left--;
             }
             moved = 1;
@@ -199,6 +232,7 @@ int main(int argc, char **argv)
     zc = argc > 4 ? atoi(argv[4]) : 16;
     unsigned rng = argc > 5 ? (unsigned)atoi(argv[5]) : 1u;
     const int dlead = argc > 6 ? atoi(argv[6]) : 0;
+    skip_mode = argc > 7 ? atoi(argv[7]) : 0;
     lead_x = 6 + dlead; lead_y = BY + 4 + dlead;
     if (nx % BX) { printf("nx must be a multiple of 8\n"); return 2; }
     nxy = (long)nx * ny;
@@ -233,11 +267,13 @@ int main(int argc, char **argv)
         b->ey = b->y_hi - b->y_lo + 1; b->ez = b->z_hi - b->z_lo + 1;
         b->L = malloc(sizeof(double) * (BX + 2) * (BY + 2) * (b->ez + 2));
         b->have = malloc((size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
+        b->last_changed = 7;   /* "changed in the sweep before the first one": nothing is skipped at the start */
     }
     long stalls = 0;
     int it;
     for (it = 1; it <= maxit; it++) {
         memcpy(u0, u, sizeof(double) * n);
+        gsweep0 = 8L * it;
         stalls += iteration(bk, nb, &rng);
         long lconv = 0;
         for (long i = 0; i < n; i++) if (fabs(u0[i] - u[i]) < tol) lconv++;
@@ -250,6 +286,6 @@ int main(int argc, char **argv)
         printf("MISMATCH nodes=%ld iters=%d ref_iters=%d ring_violations=%ld unloaded_reads=%ld\n", bad, it, ref_iters,
                ring_violations, unloaded_reads);
     else
-        printf("MATCH iters=%d stalls=%ld\n", it, stalls);
+        printf("MATCH iters=%d stalls=%ld skipped=%ld of %ld brick sweeps\n", it, stalls, skipped, tasks);
     return (bad || it != ref_iters || ring_violations || unloaded_reads) ? 1 : 0;
 }

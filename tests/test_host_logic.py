@@ -213,3 +213,11 @@ def test_brick_pipeline_leads_are_tight(brick_emu):
     """One step less lead on the upwind neighbours and the same model reads halo values too early."""
     out = subprocess.run([brick_emu, "24", "20", "22", "16", "1", "-1"], capture_output=True, text=True)
     assert out.returncode == 1 and out.stdout.startswith("MISMATCH"), out.stdout
+
+
+def test_brick_skipping_rule_is_sound_in_the_pipelined_model(brick_emu):
+    """Study for a later round: skipping a brick sweep whose inputs cannot have changed keeps
+    the oracle's bits in the pipelined, overlapped-sweep model."""
+    out = subprocess.run([brick_emu, "24", "20", "22", "16", "1", "0", "1"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("MATCH") and "skipped=" in out.stdout, out.stdout
+    assert int(out.stdout.split("skipped=")[1].split()[0]) > 0
