@@ -26,7 +26,7 @@
  * (an update whose inputs did not change is idempotent).  The model reports how many brick sweeps that skips and
  * must still give the oracle's bits.
  *
- * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead [skip]]  -> "MATCH iters=<k> stalls=<n> ..." or "MISMATCH ..."
+ * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead [skip [checkerboard cell]]]  -> "MATCH iters=<k> stalls=<n> ..." or "MISMATCH ..."
  */
 #include <float.h>
 #include <math.h>
@@ -246,7 +246,16 @@ int main(int argc, char **argv)
     unsigned char *bc = malloc(n);
     u = malloc(sizeof(double) * n);
     srand(7);
-    for (long i = 0; i < n; i++) sl[i] = 1.0 / (3000.0 + 2500.0 * (rand() / (double)RAND_MAX));
+    const int checker = argc > 8 ? atoi(argv[8]) : 0;  /* cell size of a +-10 % checkerboard instead of the random model */
+    for (long i = 0; i < n; i++) {
+        if (checker) {
+            const int ix = (int)(i % nx), iy = (int)((i / nx) % ny), iz = (int)(i / nxy);
+            const int sgn = ((ix / checker + iy / checker + iz / checker) & 1) ? -1 : 1;
+            sl[i] = 1.0 / (5000.0 * (1.0 + 0.1 * sgn));
+        } else {
+            sl[i] = 1.0 / (3000.0 + 2500.0 * (rand() / (double)RAND_MAX));
+        }
+    }
     slow = sl; lisbc = bc;
     int job = 1;
 #define DRV() oracle_eikonal3d_serial_driver(&job, &iverb, &maxit, &nsrc, &nx, &ny, &nz, &tol, &h, &x0, &y0, &z0, ts, xs, ys, zs, sl, uref, &ierr)
