@@ -57,7 +57,7 @@ struct mceik_ctx {
     fsm::BrickPlan bplan;
     int brick_zc = 256, brick_by = 8;
     // eikonal workspaces
-    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh;
+    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_faces;
     // locator state
     const float *d_tables = nullptr;
     DevBuf own_tables;
@@ -221,6 +221,13 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         fsm::launch_scale_slowness(N * nmodels, g->h, d_slow, fh, st);
         d_fh = fh;
     }
+    // compact x-face copies of every field (BrickArgs::faces), filled from u once the boundary conditions are in
+    double *d_faces = nullptr;
+    const int face_ny = (ny + 7) / 8 * 8;
+    if (bricks16 && getenv("MCEIK_FSM_FACES")) {  // measured slower so far (8-byte face stores), profiles/kernel_evolution_r2.md
+        d_faces = static_cast<double *>(ctx->ws_faces.ensure(sizeof(double) * 2 * (size_t)(nx / 8) * nz * face_ny * nfields));
+        fsm::launch_extract_faces(nx, ny, nz, face_ny, nfields, nullptr, d_u, d_faces, st);
+    }
     if (bricks)  // u0 = u before the first iteration (fsm3d.f90:60); refreshed by the convergence kernel
         MCEIK_CUDA(cudaMemcpyAsync(d_u0, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToDevice, st));
     uint8_t *d_lupd = nullptr;
@@ -256,7 +263,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
-            a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0;
+            a.faces = d_faces; a.face_ny = face_ny;
+            a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0; a.batch = 0;
             // few active fields: a publisher warp per CTA takes the release fences off the sweeping warps (+8-12 % up to
             // 11 fields, +1 % at 16, nothing beyond; profiles/kernel_evolution_r1.md)
             a.publisher = active.size() <= 16 ? 1 : 0;
@@ -266,7 +274,11 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
                 a.nf0 = (nfa + 1) / 2;
                 a.stagger = (nfa >= 12 && !getenv("MCEIK_FSM_NO_STAGGER")) ? nl / 2 : 0;  // measured: +2.5 % at 16 fields, -3.6 % at 4
                 if (a.stagger == 0) a.nf0 = nfa;  // one group holds every field
-                const std::vector<long long> vptr = host::build_ticket_table(nl, bp.h_blevel_ptr.data(), nfa, a.nf0, a.stagger);
+                a.batch = getenv("MCEIK_FSM_BATCH") ? atoi(getenv("MCEIK_FSM_BATCH")) : 0;
+                if (a.batch >= nfa) a.batch = 0;
+                if (a.batch > 0) { a.stagger = 0; a.nf0 = nfa; }
+                const std::vector<long long> vptr = a.batch > 0 ? host::build_ticket_table(nl, bp.h_blevel_ptr.data(), 1, 1, 0)
+                                                                : host::build_ticket_table(nl, bp.h_blevel_ptr.data(), nfa, a.nf0, a.stagger);
                 a.vptr = upload(ctx->ws_meta, o_vptr, vptr, st);
             }
             a.debug = getenv("MCEIK_FSM_DEBUG") ? atoi(getenv("MCEIK_FSM_DEBUG")) : 0;
@@ -475,7 +487,7 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         cudaStreamSynchronize(c->stream);
         c->plan.release();
         c->bplan.release();
-        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh,
+        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh, &c->ws_faces,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
         if (c->ev0) cudaEventDestroy(c->ev0);

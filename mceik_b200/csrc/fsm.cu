@@ -477,6 +477,32 @@ void launch_scale_slowness(size_t n, double h, const double *d_slow, double *d_o
     MCEIK_LAUNCH_CHECK();
 }
 
+__global__ void extract_faces_kernel(int nx, int ny, int nz, int face_ny, const int *__restrict__ fields,
+                                     const double *__restrict__ u, double *__restrict__ faces) {
+    const int f = fields ? fields[blockIdx.y] : blockIdx.y;
+    const int nbx = nx / 8;
+    const size_t nxy = (size_t)nx * ny, N = nxy * nz, per_side = (size_t)nbx * nz * face_ny;
+    const size_t total = 2 * (size_t)nbx * nz * ny, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        // t -> (z, y, I, side): consecutive threads read the two face columns of consecutive bricks of one grid row
+        const int side = (int)(t & 1);
+        const int I = (int)((t >> 1) % nbx);
+        const size_t r = (t >> 1) / nbx;
+        const int y = (int)(r % ny), z = (int)(r / ny);
+        faces[(size_t)f * 2 * per_side + side * per_side + ((size_t)I * nz + z) * face_ny + y] =
+            u[(size_t)f * N + (size_t)z * nxy + (size_t)y * nx + 8 * I + 7 * side];
+    }
+}
+
+void launch_extract_faces(int nx, int ny, int nz, int face_ny, int nfields, const int *d_fields, const double *d_u,
+                          double *d_faces, cudaStream_t st) {
+    if (nfields == 0) return;
+    const size_t total = 2 * (size_t)(nx / 8) * nz * ny;
+    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 148 * 4), nfields);
+    extract_faces_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, face_ny, d_fields, d_u, d_faces);
+    MCEIK_LAUNCH_CHECK();
+}
+
 __global__ void mark_bcs_kernel(int nrec, const int *__restrict__ rec_field, const int *__restrict__ rec_node,
                                 size_t n, uint8_t *__restrict__ lupd) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -34,6 +34,13 @@ namespace fsm {
 
 namespace {
 
+// timing experiments only (wrong results): -DMCEIK_DBG=bits, 1 no solver, 2 no progress waits / publications,
+// 4 no global loads, 8 no global stores (profiles/kernel_evolution_r2.md)
+#ifndef MCEIK_DBG
+#define MCEIK_DBG 0
+#endif
+constexpr int kDbg = MCEIK_DBG;
+
 constexpr int kBx = 8, kBy = 8, kNC = 2;
 constexpr int kPrefetch = 2;
 constexpr int kRing = 9 + kPrefetch;
@@ -131,6 +138,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
     }
     // progress publication of a sweeping warp (lane 0 only, after __syncwarp)
     auto publish_progress = [&](int *ptr, int val) {
+        if (kDbg & 2) return;
         if (kPub) {
             Mail &m = mail[warp];
             if (m.ptr != ptr) {  // a request for another brick may still be on its way: let it go out first
@@ -167,7 +175,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         const long long t_start = a.stats ? clock64() : 0;
 
         // ---- ticket -> virtual level -> (group, sweep, brick level, brick, field)
-        const TicketTask task = decode_ticket(t, a.vptr, a.blevel_ptr, nl, a.stagger, nf0, nf1);
+        TicketTask task;
+        if (a.batch > 0) {  // fields in batches of a.batch, one batch after the other (vptr is the one-field table)
+            const long long per = 8LL * a.nbricks * a.batch;
+            const int b = (int)(t / per);
+            const int nfb = min(a.batch, nf - b * a.batch);
+            const long long r = t - (long long)b * per;
+            task = decode_ticket(r / nfb, a.vptr, a.blevel_ptr, nl, 0, 1, 0);
+            const long long r2 = r - a.vptr[task.sweep * nl + task.level] * nfb;
+            task.bidx = (int)(r2 / nfb);
+            task.fidx = b * a.batch + (int)(r2 - (long long)task.bidx * nfb);
+        } else {
+            task = decode_ticket(t, a.vptr, a.blevel_ptr, nl, a.stagger, nf0, nf1);
+        }
         const int s = task.sweep;
         const int f = __ldg(a.active + task.fidx);
         const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + task.level) + task.bidx);
@@ -191,7 +211,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 int need = s << kProgShift;
                 if (dk != 0 && dk == (revz ? 1 : -1)) need = (s + 1) << kProgShift;
                 const int *p = done_f + ((NK * a.nby + NJ) * a.nbx + NI);
-                while (ld_acquire_gpu(p) < need) __nanosleep(400);
+                if (!(kDbg & 2))
+                    while (ld_acquire_gpu(p) < need) __nanosleep(400);
             }
         }
         if (lane < 2) {
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         int seen = 0, ahead = 0;
         auto wait_upwind = [&](int steps_needed) {
             const long long t0 = a.stats ? clock64() : 0;
-            if (up_ptr) {
+            if (up_ptr && !(kDbg & 2)) {
                 // lane 0 watches the upwind x neighbour, lane 1 the upwind y neighbour.  A slot's y-halo row is the
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
@@ -273,6 +294,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         // 2 clamped single column (brick on the grid's x face: the halo repeats the boundary column)
         int hmode = 0, kofs_h = 0, cu_h = 0;
         const double *pu_h = uf;
+        // x-face copies (BrickArgs::faces): hmode 3 = one 8-byte copy per row from the neighbour's face column copy
+        // (the brick's own copy where the halo is the clamped boundary column, fsm3d.f90:495-499)
+        const bool use_faces = a.faces != nullptr;
+        const size_t per_side = (size_t)a.nbx * nz * a.face_ny;
+        double *ffaces = use_faces ? a.faces + (size_t)f * 2 * per_side : nullptr;
+        const long long fzstride = (long long)sz * a.face_ny;
         if (lane < 16) {
             const bool left = lane < 8;
             const int hj = lane & 7;
@@ -281,7 +308,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             const size_t row = (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx;
             const bool inside = left ? x_lo >= 2 : x_lo + kBx + 1 <= nx - 1;
             if (hj < ey) {
-                if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); pu_h = uf + row + (left ? x_lo - 2 : x_lo + kBx); }
+                if (use_faces && !(kDbg & 32)) {
+                    const bool in_f = left ? I > 0 : I < a.nbx - 1;
+                    const int side = left ? (in_f ? 1 : 0) : (in_f ? 0 : 1);
+                    const int In = left ? (in_f ? I - 1 : I) : (in_f ? I + 1 : I);
+                    hmode = 3; cu_h = (hj + 1) * kURow + (left ? 1 : 10);
+                    pu_h = ffaces + side * per_side + ((size_t)In * nz + zb) * a.face_ny + min(max(yb + sy * hj, 0), ny - 1);
+                } else if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); pu_h = uf + row + (left ? x_lo - 2 : x_lo + kBx); }
                 else { hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10); pu_h = uf + row + (left ? x_lo : x_lo + kBx - 1); }
             }
         } else if (lane < 24) {
@@ -300,13 +333,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         const long long zsb = zstride * (long long)sizeof(double);
         long long zo = -(long long)kofs_t * zsb;                            // (ld_m - kofs_t) planes
         const char *bu_t = reinterpret_cast<const char *>(pu_t), *bf_t = reinterpret_cast<const char *>(pf_t);
-        const char *bu_h = reinterpret_cast<const char *>(pu_h) + (long long)(kofs_t - kofs_h) * zsb;  // halo pair of the same issue
+        // halo transfer of the same issue; face copies (hmode 3) advance by the face plane stride (running offset zoh)
+        const long long fzsb = fzstride * (long long)sizeof(double);
+        long long zoh = -(long long)kofs_t * fzsb;
+        const char *bu_h = reinterpret_cast<const char *>(pu_h) + (long long)(kofs_t - kofs_h) * (hmode == 3 ? fzsb : zsb);
         char *bu_st = reinterpret_cast<char *>(pu_t) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
+        // this lane's own face entry (lanes holding memory column 0 or 7 of row jt), written with the pair
+        const bool face_lane = use_faces && (tp == 0 || tp == 3) && act_t && !(kDbg & 16);
+        double *pf_st = face_lane ? ffaces + (tp == 0 ? 0 : 1) * per_side + ((size_t)I * nz + zb) * a.face_ny + (yb + sy * jt) : nullptr;
+        char *bf_st = reinterpret_cast<char *>(pf_st) - (8 + kPrefetch) * fzsb;
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
             const int k = ld_m - kofs_t;
-            if (kSteady) {
+            if (kDbg & 4) {
+            } else if (kSteady) {
                 cp_async16(sp + cu_t, bu_t + zo);
                 cp_async16(sp + cf_t, bf_t + zo);
             } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
@@ -315,16 +356,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + z);
             }
             const int kh = ld_m - kofs_h;
-            if (kSteady) {  // full brick off the x faces: every halo lane copies a pair
-                if (hmode != 0) cp_async16(sp + cu_h, bu_h + zo);
+            if (kDbg & 4) {
+            } else if (kSteady) {  // full brick: every halo lane copies a pair of u (a face entry with face copies)
+                if (hmode == 3) cp_async8(sp + cu_h, bu_h + zoh);
+                else if (hmode != 0) cp_async16(sp + cu_h, bu_h + zo);
             } else if (hmode == 1) {
                 if (kh >= 0 && kh < ez) cp_async16(sp + cu_h, pu_h + (long long)kh * zstride);
             } else if (hmode == 2) {
                 if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * zstride);
+            } else if (hmode == 3) {
+                if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * fzstride);
             }
             cp_async_commit();
             ++ld_m;
             zo += zsb;
+            zoh += fzsb;
             ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
         };
         for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot(std::false_type());
@@ -389,7 +435,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 uz[c] = dmin2(zm[c], zp[c]);
                 fh[c] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
             }
-            local_solve_xn<kNC>(ux, uy, uz, fh, go, nv);
+            if (kDbg & 1) {
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) nv[c] = __dadd_rn(__dadd_rn(ux[c], uy[c]), __dadd_rn(uz[c], fh[c]));
+            } else {
+                local_solve_xn<kNC>(ux, uy, uz, fh, go, nv);
+            }
 #pragma unroll
             for (int c = 0; c < kNC; ++c) {
                 const bool upd = go[c] && nv[c] < self[c];  // u = MIN(u, ubar) (fsm3d.f90:477)
@@ -402,10 +453,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             // slot l - 3 is final: write its pair of this lane back (one 16-byte store)
             {
                 const int ks = l - 3 - kofs_t;
-                if (kSteady || (act_t && (unsigned)ks < (unsigned)ez)) {
+                if (!(kDbg & 8) && (kSteady || (act_t && (unsigned)ks < (unsigned)ez))) {
                     const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + cu_t);
                     if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st + zo), v);
                     else __stcg(reinterpret_cast<double2 *>(pu_t + (long long)ks * zstride), v);
+                    if (face_lane) {
+                        const double fv = tp == 0 ? v.x : v.y;
+                        if (kSteady) __stcg(reinterpret_cast<double *>(bf_st + zoh), fv);
+                        else __stcg(pf_st + (long long)ks * fzstride, fv);
+                    }
                 }
             }
             om = oc; oc = op;
@@ -428,7 +484,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         // steady window: all transfers, updates and stores of the step touch in-brick nodes of a full
         // brick that is not on the grid's x faces and holds no boundary-condition node; it runs in whole
         // publication chunks with no per-step bookkeeping
-        const bool full = ey == kBy && !hasbc && x_lo >= 2 && x_lo + kBx + 1 <= nx - 1;
+        const bool full = ey == kBy && !hasbc && ((use_faces && !(kDbg & 32)) || (x_lo >= 2 && x_lo + kBx + 1 <= nx - 1));
         int s_lo = (kBy + 6 + publish - 1) & ~(publish - 1), s_hi = (ez - 3 - kPrefetch) & ~(publish - 1);
         if (!full || s_hi <= s_lo) s_lo = s_hi = nsteps;
         int l = 0;

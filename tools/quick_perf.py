@@ -27,6 +27,7 @@ ap.add_argument("--gs-events", type=int, default=512)
 ap.add_argument("--skip-fsm", action="store_true")
 ap.add_argument("--algo", type=int, default=0)
 ap.add_argument("--skip-gs", action="store_true")
+ap.add_argument("--maxit", type=int, default=20)
 a = ap.parse_args()
 
 torch.cuda.set_device(0)
@@ -40,7 +41,7 @@ if not a.skip_fsm:
     slow = torch.from_numpy(cases.checkerboard_slowness(n, n, n, cell=max(n // 8, 1))).cuda()
     xs, ys, zs = cases.interior_sources(a.fields, n, n, n, h, seed=3)
     d_u = torch.empty((a.fields, N), dtype=torch.float64, device="cuda")
-    sol = EikonalSolver(ctx, n, n, n, h, algo=a.algo)
+    sol = EikonalSolver(ctx, n, n, n, h, algo=a.algo, maxit=a.maxit)
     for rep in range(a.reps):
         torch.cuda.synchronize()
         t = time.time()
