@@ -16,6 +16,11 @@ class Context:
             raise _lib.MceikError(f"mceik_ctx_create failed (rc={rc}): {_lib.last_error()}")
         self.handle = h
 
+    def set_tuning(self, key, value):
+        """Development switch of the sweep / search kernels (``mceik_fsm_set_tuning``); returns the context."""
+        _lib.check(self._lib.mceik_fsm_set_tuning(self.handle, key.encode(), int(value)), "mceik_fsm_set_tuning")
+        return self
+
     def synchronize(self):
         _lib.check(self._lib.mceik_ctx_synchronize(self.handle), "mceik_ctx_synchronize")
 

@@ -55,7 +55,22 @@ struct mceik_ctx {
     std::vector<char> early_done;
     fsm::TilePlan plan;
     fsm::BrickPlan bplan;
-    int brick_zc = 256, brick_by = 8;
+    // development switches of the sweep kernels: defaults are the measured best; read from the environment once when
+    // the context is created (MCEIK_FSM_<KEY>), changed per context with mceik_fsm_set_tuning().  -1 = automatic.
+    struct Tuning {
+        int zc = 256;         // planes per brick (<= 256)
+        int by = 8;           // 16: 8x16 cross-section, generic brick kernel
+        int no16 = 0;         // 1: generic brick kernel even when nx % 8 == 0
+        int publish = -1;     // steps between progress publications (power of two)
+        int publisher = -1;   // 0 / 1: force one publication flavour
+        int no_stagger = 0;   // 1: one field group in the ticket order
+        int pair_min = 24;    // two fields per task from this many active fields on (0 = never)
+        int faces = 0;        // 1: compact x-face copies (BrickArgs::faces)
+        int l2pf = 0;         // planes prefetched into the L2 ahead of the ring (0 = off)
+        int batch = 0;        // sequential field batches (experiment)
+        int trace = 0, stats = 0, debug = 0;
+        int locate_no_align = 0;  // 1: keep ragged event blocks on the general search kernel (MCEIK_LOCATE_NO_ALIGN)
+    } tune;
     // eikonal workspaces
     DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_faces;
     // locator state
@@ -68,6 +83,25 @@ struct mceik_ctx {
 };
 
 namespace {
+
+int *tuning_slot(mceik_ctx *c, const char *key) {
+    struct { const char *name; int *p; } const tab[] = {
+        {"ZC", &c->tune.zc}, {"BY", &c->tune.by}, {"NO16", &c->tune.no16}, {"PUBLISH", &c->tune.publish},
+        {"PUBLISHER", &c->tune.publisher}, {"NO_STAGGER", &c->tune.no_stagger}, {"PAIR_MIN", &c->tune.pair_min},
+        {"FACES", &c->tune.faces}, {"L2PF", &c->tune.l2pf}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
+        {"STATS", &c->tune.stats}, {"DEBUG", &c->tune.debug}, {"LOCATE_NO_ALIGN", &c->tune.locate_no_align}};
+    for (const auto &e : tab)
+        if (strcmp(e.name, key) == 0) return e.p;
+    return nullptr;
+}
+void tuning_from_env(mceik_ctx *c) {
+    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "PAIR_MIN", "FACES", "L2PF", "BATCH", "TRACE",
+                          "STATS", "DEBUG"}) {
+        const std::string name = std::string("MCEIK_FSM_") + k;
+        if (const char *e = getenv(name.c_str())) *tuning_slot(c, k) = atoi(e);
+    }
+    if (const char *e = getenv("MCEIK_LOCATE_NO_ALIGN")) c->tune.locate_no_align = atoi(e);
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -145,7 +179,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     ctx->plan.build(nx, ny, nz, st);
     const fsm::TilePlan &pl = ctx->plan;
     const bool bricks = ctx->fsm_algo == MCEIK_FSM_ALGO_BRICKS;
-    if (bricks) ctx->bplan.build(nx, ny, nz, ctx->brick_by, ctx->brick_zc, st);
+    if (bricks) ctx->bplan.build(nx, ny, nz, ctx->tune.by == 16 ? 16 : 8, std::max(1, std::min(256, ctx->tune.zc)), st);
     const fsm::BrickPlan &bp = ctx->bplan;
 
     // ---- boundary conditions: stencil records per field (host), unique node lists per field
@@ -186,7 +220,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     const size_t o_recf = take(sizeof(int) * std::max<size_t>(rec_field.size(), 1));
     const size_t o_recn = take(sizeof(int) * std::max<size_t>(rec_node.size(), 1));
     const size_t o_gfields = take(sizeof(int) * fsm::kMaxSlots * nfields), o_gmodel = take(sizeof(int) * nfields);
-    const size_t o_active = take(sizeof(int) * nfields);
+    const size_t o_active = take(sizeof(int) * nfields), o_units = take(sizeof(int) * nfields);
     const size_t o_vptr = take(sizeof(long long) * (8 * (size_t)std::max(bp.nblevels, 1) + std::max(bp.nblevels, 1) + 2));
     ctx->ws_meta.ensure(off);
     const int *d_fmodel = upload(ctx->ws_meta, o_fmodel, fmodel, st);
@@ -214,7 +248,17 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     std::vector<unsigned long long> h_nonconv(nfields);
 
     // the 16-byte-pair brick kernel reads slow*h, formed once per solve instead of once per node visit
-    const bool bricks16 = bricks && nx % 8 == 0 && bp.by == 8 && !getenv("MCEIK_FSM_NO16");
+    bool bricks16 = bricks && nx % 8 == 0 && bp.by == 8 && !ctx->tune.no16;
+    if (bricks16) {  // its per-brick list of boundary-condition planes is short: fields with many sources stacked in one brick
+        std::map<std::pair<int, int>, std::vector<int>> planes;  // (field, brick) -> planes holding stencil nodes
+        for (size_t r = 0; r < rec_node.size(); ++r) {
+            const int node = rec_node[r], gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
+            std::vector<int> &v = planes[{rec_field[r], ((gz / bp.zc) * bp.nby + gy / bp.by) * bp.nbx + gx / 8}];
+            if (std::find(v.begin(), v.end(), gz) == v.end()) v.push_back(gz);
+        }
+        for (auto &kv : planes)
+            if ((int)kv.second.size() > fsm::bricks16_max_bc_planes()) bricks16 = false;  // -> generic brick kernel
+    }
     const double *d_fh = nullptr;
     if (bricks16) {
         double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * N * nmodels));
@@ -224,7 +268,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     // compact x-face copies of every field (BrickArgs::faces), filled from u once the boundary conditions are in
     double *d_faces = nullptr;
     const int face_ny = (ny + 7) / 8 * 8;
-    if (bricks16 && getenv("MCEIK_FSM_FACES")) {  // measured slower so far (8-byte face stores), profiles/kernel_evolution_r2.md
+    if (bricks16 && ctx->tune.faces) {  // measured slower so far (8-byte face stores), profiles/kernel_evolution_r2.md
         d_faces = static_cast<double *>(ctx->ws_faces.ensure(sizeof(double) * 2 * (size_t)(nx / 8) * nz * face_ny * nfields));
         fsm::launch_extract_faces(nx, ny, nz, face_ny, nfields, nullptr, d_u, d_faces, st);
     }
@@ -246,17 +290,31 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
                                          d_u, st);
             fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
         } else if (bricks) {
-            const int *d_active = upload(ctx->ws_meta, o_active, active, st);
+            // many active fields: two fields of one slowness model per task (BrickArgs::fields_per_task)
+            const bool pairs = bricks16 && ctx->tune.pair_min > 0 && (int)active.size() >= ctx->tune.pair_min;
+            std::vector<int> units;
+            if (pairs) {
+                std::map<int, std::vector<int>> by_model;
+                for (int f : active) by_model[fmodel[f]].push_back(f);
+                for (auto &kv : by_model)
+                    for (size_t i = 0; i < kv.second.size(); i += 2)
+                        units.push_back(kv.second[i] | (kv.second[i + 1 < kv.second.size() ? i + 1 : i] << 16));
+            } else {
+                units = active;
+            }
+            const int *d_active = upload(ctx->ws_meta, o_active, active, st);  // convergence test: plain field ids
+            const int *d_units = upload(ctx->ws_meta, o_units, units, st);
             fsm::BrickArgs a;
             a.nx = nx; a.ny = ny; a.nz = nz;
             a.nbx = bp.nbx; a.nby = bp.nby; a.nbz = bp.nbz; a.nbricks = bp.nbricks; a.nblevels = bp.nblevels; a.zc = bp.zc; a.by = bp.by;
-            a.nfields_active = (int)active.size();
+            a.nfields_active = (int)units.size();
+            a.fields_per_task = pairs ? 2 : 1;
             // few fields: short publication interval (tight pipelining of the brick wavefront);
             // many fields: parallelism is plentiful, publish less often (each publication costs a fence)
             a.publish = active.size() >= 48 ? 16 : (active.size() > 16 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
-            if (const char *e = getenv("MCEIK_FSM_PUBLISH")) a.publish = atoi(e);
+            if (ctx->tune.publish > 0) a.publish = ctx->tune.publish;
             a.h = g->h;
-            a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
+            a.active = d_units; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
             a.u = d_u;
             a.brick_order = ctx->bplan.brick_order.as<int>();
             a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
@@ -264,25 +322,26 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
             a.faces = d_faces; a.face_ny = face_ny;
+            a.l2_prefetch = ctx->tune.l2pf;
             a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0; a.batch = 0;
             // few active fields: a publisher warp per CTA takes the release fences off the sweeping warps (+8-12 % up to
             // 11 fields, +1 % at 16, nothing beyond; profiles/kernel_evolution_r1.md)
-            a.publisher = active.size() <= 16 ? 1 : 0;
-            if (const char *e = getenv("MCEIK_FSM_PUBLISHER")) a.publisher = atoi(e) != 0;
+            a.publisher = active.size() <= 16 && !pairs ? 1 : 0;
+            if (ctx->tune.publisher >= 0 && !pairs) a.publisher = ctx->tune.publisher != 0;
             if (bricks16) {  // two field groups half a sweep apart (see BrickArgs)
                 const int nl = bp.nblevels, nfa = a.nfields_active;
                 a.nf0 = (nfa + 1) / 2;
-                a.stagger = (nfa >= 12 && !getenv("MCEIK_FSM_NO_STAGGER")) ? nl / 2 : 0;  // measured: +2.5 % at 16 fields, -3.6 % at 4
+                a.stagger = (nfa >= 12 && !ctx->tune.no_stagger) ? nl / 2 : 0;  // measured: +2.5 % at 16 fields, -3.6 % at 4
                 if (a.stagger == 0) a.nf0 = nfa;  // one group holds every field
-                a.batch = getenv("MCEIK_FSM_BATCH") ? atoi(getenv("MCEIK_FSM_BATCH")) : 0;
+                a.batch = ctx->tune.batch;
                 if (a.batch >= nfa) a.batch = 0;
                 if (a.batch > 0) { a.stagger = 0; a.nf0 = nfa; }
                 const std::vector<long long> vptr = a.batch > 0 ? host::build_ticket_table(nl, bp.h_blevel_ptr.data(), 1, 1, 0)
                                                                 : host::build_ticket_table(nl, bp.h_blevel_ptr.data(), nfa, a.nf0, a.stagger);
                 a.vptr = upload(ctx->ws_meta, o_vptr, vptr, st);
             }
-            a.debug = getenv("MCEIK_FSM_DEBUG") ? atoi(getenv("MCEIK_FSM_DEBUG")) : 0;
-            a.stats = getenv("MCEIK_FSM_STATS") ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
+            a.debug = ctx->tune.debug;
+            a.stats = ctx->tune.stats ? reinterpret_cast<unsigned long long *>(ctrl + 64) : nullptr;
             MCEIK_CUDA(cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)nfields * bp.nbricks, st));
             MCEIK_CUDA(cudaEventRecord(ctx->ev0, st));
             if (bricks16) fsm::launch_iteration_bricks16(a, st);
@@ -330,7 +389,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         MCEIK_CUDA(cudaMemcpyAsync(h_nonconv.data(), d_nonconv, sizeof(unsigned long long) * nfields,
                                    cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaStreamSynchronize(st));
-        if (bricks && getenv("MCEIK_FSM_STATS")) {
+        if (bricks && ctx->tune.stats) {
             unsigned long long hs[4];
             MCEIK_CUDA(cudaMemcpy(hs, ctrl + 64, sizeof(hs), cudaMemcpyDeviceToHost));
             if (hs[3]) printf("[fsm stats] iter %d: tasks %llu  avg cycles: start-wait %.0f  upwind-wait %.0f  run %.0f\n", k, hs[3],
@@ -340,7 +399,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             float ms = 0.f;
             MCEIK_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
             ctx->last_sweep_ms += ms;
-            if (getenv("MCEIK_FSM_TRACE")) printf("[fsm trace] iter %d: %zu active fields, sweep kernel %.2f ms\n", k, active.size(), ms);
+            if (ctx->tune.trace) printf("[fsm trace] iter %d: %zu active fields, sweep kernel %.2f ms\n", k, active.size(), ms);
         }
         std::vector<int> still;
         for (int f : active) {
@@ -469,6 +528,7 @@ int mceik_ctx_create(int device, void *stream, mceik_ctx **out) {
         if (!getenv("MCEIK_L2_FETCH_DEFAULT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
         mceik_ctx *c = new mceik_ctx();
         c->device = device;
+        tuning_from_env(c);
         if (stream) {
             c->stream = static_cast<cudaStream_t>(stream);
         } else {
@@ -511,8 +571,16 @@ int mceik_ctx_synchronize(mceik_ctx *c) {
 int mceik_fsm_set_algo(mceik_ctx *c, int algo) {
     if (!c || (algo != MCEIK_FSM_ALGO_TILES && algo != MCEIK_FSM_ALGO_LEVELS && algo != MCEIK_FSM_ALGO_BRICKS)) return -1;
     c->fsm_algo = algo;
-    if (const char *e = getenv("MCEIK_FSM_ZC")) c->brick_zc = std::max(1, std::min(256, atoi(e)));
-    if (const char *e = getenv("MCEIK_FSM_BY")) c->brick_by = atoi(e) == 16 ? 16 : 8;
+    return 0;
+}
+
+int mceik_fsm_set_tuning(mceik_ctx *c, const char *key, int value) {
+    int *p = (c && key) ? tuning_slot(c, key) : nullptr;
+    if (!p) {
+        set_error("mceik_fsm_set_tuning: unknown key");
+        return -1;
+    }
+    *p = value;
     return 0;
 }
 long long mceik_fsm_last_node_updates(mceik_ctx *c) { return c ? c->last_updates : 0; }
@@ -703,7 +771,7 @@ int mceik_locate_batched_host(mceik_ctx *ctx, int job, int nevents, const int *o
             if (table_id[obs_ptr[0] + p] >= ctx->ntables) { set_error("mceik_locate_batched_host: table id out of range"); return -1; }
         std::vector<int> optr2, tid2;
         std::vector<double> tobs2, var2;
-        if (np > 0 && !getenv("MCEIK_LOCATE_NO_ALIGN")) {
+        if (np > 0 && !ctx->tune.locate_no_align) {
             host::align_event_blocks(gs::kEventsPerBlock, nevents, optr.data(), table_id + obs_ptr[0], tobs_cor + obs_ptr[0], varobs + obs_ptr[0], optr2, tid2,
                                tobs2, var2);
             if (tid2.size() != (size_t)np || optr2 != optr) {  // some block was re-laid out: continue with the aligned picks

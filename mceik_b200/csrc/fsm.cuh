@@ -75,7 +75,9 @@ struct BrickPlan {
 struct BrickArgs {
     int nx, ny, nz;
     int nbx, nby, nbz, nbricks, nblevels, zc, by;
-    int nfields_active;
+    int nfields_active;       // bricks16: number of tasks' worth of fields = entries of `active` (pairs count once)
+    int fields_per_task;      // bricks16: 1, or 2 = active[] holds f0 | f1 << 16, two fields of one slowness model
+                              // walked together (f1 == f0: a single field); other kernels: 1
     int publish;              // a sweeping warp publishes its progress every `publish` steps (4, 8 or 16; a power of two)
     double h;
     const int *active;        // [nfields_active] field ids
@@ -98,6 +100,7 @@ struct BrickArgs {
     // its own copies up to date when it writes u back.  nullptr = halo columns are read from u.
     double *faces;
     int face_ny;
+    int l2_prefetch;              // bricks16: planes ahead of the ring's own loads that are prefetched into the L2 (0 = off)
     int batch;                    // bricks16 experiment (MCEIK_FSM_BATCH): > 0 = fields run in sequential batches of this size
     int publisher;                // bricks16: 1 = the last warp of every CTA publishes progress for the others
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
@@ -138,6 +141,8 @@ __host__ __device__ inline TicketTask decode_ticket(long long t, const long long
 }
 // 16-byte-pair variant (fsm_bricks16.cu): requires nx % 8 == 0 and by == 8
 void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st);
+// most planes of one brick that may hold boundary-condition nodes of one field (more: use launch_iteration_bricks)
+int bricks16_max_bc_planes();
 
 // device self-test of sqrt_fast / local_solve_sl against __dsqrt_rn / local_solve; d_bad[2] counts mismatches
 void launch_selftest(unsigned long long seed, int blocks, int per_thread, unsigned long long *d_bad, cudaStream_t st);

@@ -46,12 +46,20 @@ constexpr int kPrefetch = 2;
 constexpr int kRing = 9 + kPrefetch;
 constexpr int kURow = 12;                          // row: [pad(-2) halo(-1) | 0..7 | halo(8) pad(9)]
 constexpr int kUCells = kURow * (kBy + 2);
-constexpr int kSlot = kUCells + kBx * kBy;         // 184 doubles, 16-byte aligned
 constexpr int kMaxZc = 256;
-constexpr int kWarps = 12;
 constexpr int kProgShift = 12;
 constexpr int kLead = kBy + 3;
-constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + sizeof(unsigned long long) * kMaxZc;
+constexpr int kBcMax = 16;                         // planes of one brick that hold boundary-condition nodes of one field
+// kNF fields of one slowness model walk the same brick in one task (template parameter of the kernel): their ring
+// slots sit side by side ([field 0 rows][field 1 rows][slowness]), the slowness tile is loaded once, every address
+// and every wait / publication is shared, and a lane advances 2 * kNF independent update chains.
+template <int kNF>
+struct Cfg {
+    static constexpr int kWarps = kNF == 2 ? 8 : 12;
+    static constexpr int kSlot = kNF * kUCells + kBx * kBy;  // 184 / 304 doubles, 16-byte aligned
+    static constexpr int kBcBytes = kNF * kBcMax * 16;       // [kNF][kBcMax] masks (8 B), then [kNF][kBcMax] planes (4 B, padded)
+    static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + kBcBytes;
+};
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -61,6 +69,7 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -99,8 +108,10 @@ __device__ __forceinline__ void st_relaxed_gpu(int *p, int v) {
 
 }  // namespace
 
-template <bool kPub>
-__global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
+template <bool kPub, int kNF>
+__global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
+    constexpr int kWarps = Cfg<kNF>::kWarps, kSlot = Cfg<kNF>::kSlot, kNQ = kNF * kNC;
+    constexpr size_t kWarpSmem = Cfg<kNF>::kWarpSmem;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ Mail mail[kWarps];
@@ -152,7 +163,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         }
     };
     double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
-    unsigned long long *bcm = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kMaxZc]
+    unsigned long long *bc_mask = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kNF][kBcMax]
+    int *bc_plane = reinterpret_cast<int *>(bc_mask + kNF * kBcMax);                           // [kNF][kBcMax], -1 = free
 
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const size_t nxy = (size_t)nx * ny, N = nxy * nz;
@@ -189,7 +201,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             task = decode_ticket(t, a.vptr, a.blevel_ptr, nl, a.stagger, nf0, nf1);
         }
         const int s = task.sweep;
-        const int f = __ldg(a.active + task.fidx);
+        // the task's fields: active[] holds f0 | f1 << 16 when kNF == 2 (f1 == f0: a single field, whose second copy
+        // is computed from the same inputs and never stored)
+        const int unit = __ldg(a.active + task.fidx);
+        int fld[kNF];
+        fld[0] = unit & 0xffff;
+        if (kNF == 2) fld[kNF - 1] = (unit >> 16) & 0xffff;
+        const int f = fld[0];
+        const bool st_second = kNF == 2 && fld[kNF - 1] != fld[0];
         const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + task.level) + task.bidx);
         const bool revx = (s & 1) != 0, revy = (s & 2) != 0, revz = (s & 4) != 0;  // fsm3d.f90:46-53
         int I = packed & 1023, J = (packed >> 10) & 1023, K = packed >> 20;
@@ -248,34 +267,51 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         const int ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
         const int yb = revy ? y_hi : y_lo, zb = revz ? z_hi : z_lo;
         const int sx = revx ? -1 : 1, sy = revy ? -1 : 1, sz = revz ? -1 : 1;
-        double *uf = a.u + (size_t)f * N;
+        double *ufs[kNF];
+#pragma unroll
+        for (int fi = 0; fi < kNF; ++fi) ufs[fi] = a.u + (size_t)fld[fi] * N;
         const double *sl = a.slow + (size_t)__ldg(a.field_model + f) * N;
 
-        // ---- boundary-condition nodes inside the brick (bit = j * 8 + i in sweep coordinates)
+        // ---- boundary-condition nodes inside the brick: per field a short list of (plane, 64-bit mask) with
+        // bit = j * 8 + i in sweep coordinates (at most kBcMax planes per field and brick; the host checks)
         bool hasbc = false;
-        {
-            const int b0 = __ldg(a.bc_ptr + f), b1 = __ldg(a.bc_ptr + f + 1);
+#pragma unroll
+        for (int fi = 0; fi < kNF; ++fi) {
+            const int b0 = __ldg(a.bc_ptr + fld[fi]), b1 = __ldg(a.bc_ptr + fld[fi] + 1);
             bool mine = false;
             for (int n = b0 + lane; n < b1; n += 32) {
                 const int node = __ldg(a.bc_node + n);
                 const int gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
                 mine |= gx >= x_lo && gx < x_lo + kBx && gy >= y_lo && gy <= y_hi && gz >= z_lo && gz <= z_hi;
             }
-            hasbc = __any_sync(0xffffffffu, mine);
-            if (hasbc) {
-                for (int k = lane; k < kMaxZc; k += 32) bcm[k] = 0ULL;
-                __syncwarp();
+            hasbc = __any_sync(0xffffffffu, mine) || hasbc;
+        }
+        if (hasbc) {
+            for (int e = lane; e < kNF * kBcMax; e += 32) { bc_mask[e] = 0ULL; bc_plane[e] = -1; }
+            __syncwarp();
+#pragma unroll
+            for (int fi = 0; fi < kNF; ++fi) {
+                const int b0 = __ldg(a.bc_ptr + fld[fi]), b1 = __ldg(a.bc_ptr + fld[fi] + 1);
                 for (int n = b0 + lane; n < b1; n += 32) {
                     const int node = __ldg(a.bc_node + n);
                     const int gx = node % nx, gy = (node / nx) % ny, gz = node / (nx * ny);
                     if (gx >= x_lo && gx < x_lo + kBx && gy >= y_lo && gy <= y_hi && gz >= z_lo && gz <= z_hi) {
                         const int i = revx ? x_lo + kBx - 1 - gx : gx - x_lo, j = (gy - yb) * sy, k = (gz - zb) * sz;
-                        atomicOr(bcm + k, 1ULL << (j * kBx + i));
+                        for (int e = 0; e < kBcMax; ++e) {  // claim or find the entry of plane k
+                            const int old = atomicCAS(bc_plane + fi * kBcMax + e, -1, k);
+                            if (old == -1 || old == k) { atomicOr(bc_mask + fi * kBcMax + e, 1ULL << (j * kBx + i)); break; }
+                        }
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         }
+        auto is_bc = [&](int fi, int k, int bit) {  // rare path (bricks holding a source)
+            unsigned long long m = 0ULL;
+            for (int e = 0; e < kBcMax; ++e)
+                if (bc_plane[fi * kBcMax + e] == k) m = bc_mask[fi * kBcMax + e];
+            return ((m >> bit) & 1ULL) != 0ULL;
+        };
 
         // ---- transfer descriptors of this lane (all per task): interior pair, slowness pair, halo pair
         const long long zstride = (long long)sz * (long long)nxy;
@@ -285,20 +321,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         const int gi = xgroup(revx ? kBx - 1 - 2 * tp : 2 * tp);
         const int kofs_t = gi + jt + 2;
         const size_t rowt = (size_t)zb * nxy + (size_t)min(max(yb + sy * jt, 0), ny - 1) * nx + x_lo + 2 * tp;
-        double *pu_t = uf + rowt;
         const double *pf_t = sl + rowt;
-        const int cu_t = (jt + 1) * kURow + 2 * tp + 2, cf_t = kUCells + jt * kBx + 2 * tp;
+        // ring cells: field fi's rows start at fi * kUCells, the slowness tile follows the last field
+        const int cu_t = (jt + 1) * kURow + 2 * tp + 2, cf_t = kNF * kUCells + jt * kBx + 2 * tp;
         const bool act_t = jt < ey;
         // halo pair of lanes 0..23: 0-7 left x pair (q = -2,-1) of row h; 8-15 right x pair (q = 8,9) of row
         // h-8; 16-19 row j = -1, pair h-16; 20-23 row j = By, pair h-20.  hmode: 0 none, 1 pair copy,
         // 2 clamped single column (brick on the grid's x face: the halo repeats the boundary column)
         int hmode = 0, kofs_h = 0, cu_h = 0;
-        const double *pu_h = uf;
+        size_t offh = 0;  // offset of the halo transfer's source inside a field (or inside a field's face copies)
         // x-face copies (BrickArgs::faces): hmode 3 = one 8-byte copy per row from the neighbour's face column copy
         // (the brick's own copy where the halo is the clamped boundary column, fsm3d.f90:495-499)
         const bool use_faces = a.faces != nullptr;
         const size_t per_side = (size_t)a.nbx * nz * a.face_ny;
-        double *ffaces = use_faces ? a.faces + (size_t)f * 2 * per_side : nullptr;
         const long long fzstride = (long long)sz * a.face_ny;
         if (lane < 16) {
             const bool left = lane < 8;
@@ -313,9 +348,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                     const int side = left ? (in_f ? 1 : 0) : (in_f ? 0 : 1);
                     const int In = left ? (in_f ? I - 1 : I) : (in_f ? I + 1 : I);
                     hmode = 3; cu_h = (hj + 1) * kURow + (left ? 1 : 10);
-                    pu_h = ffaces + side * per_side + ((size_t)In * nz + zb) * a.face_ny + min(max(yb + sy * hj, 0), ny - 1);
-                } else if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); pu_h = uf + row + (left ? x_lo - 2 : x_lo + kBx); }
-                else { hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10); pu_h = uf + row + (left ? x_lo : x_lo + kBx - 1); }
+                    offh = side * per_side + ((size_t)In * nz + zb) * a.face_ny + min(max(yb + sy * hj, 0), ny - 1);
+                } else if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); offh = row + (left ? x_lo - 2 : x_lo + kBx); }
+                else { hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10); offh = row + (left ? x_lo : x_lo + kBx - 1); }
             }
         } else if (lane < 24) {
             const bool low = lane < 20;
@@ -325,47 +360,74 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             kofs_h = gh + hj + 2;
             hmode = 1;
             cu_h = (hj + 1) * kURow + 2 * hp + 2;
-            pu_h = uf + (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx + x_lo + 2 * hp;
+            offh = (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx + x_lo + 2 * hp;
+        }
+        // per-field bases of the three transfers of this lane: interior pair (loaded and written back), halo source
+        double *pu_t[kNF];
+        const double *pu_h[kNF];
+        double *pf_st[kNF];  // own face entry (lanes holding memory column 0 or 7 of row jt), written with the pair
+        const bool face_lane = use_faces && (tp == 0 || tp == 3) && act_t && !(kDbg & 16);
+#pragma unroll
+        for (int fi = 0; fi < kNF; ++fi) {
+            pu_t[fi] = ufs[fi] + rowt;
+            double *ffaces = use_faces ? a.faces + (size_t)fld[fi] * 2 * per_side : nullptr;
+            pu_h[fi] = (hmode == 3 ? ffaces : ufs[fi]) + offh;
+            pf_st[fi] = face_lane ? ffaces + (tp == 0 ? 0 : 1) * per_side + ((size_t)I * nz + zb) * a.face_ny + (yb + sy * jt) : nullptr;
         }
 
         int ld_slot = 0, ld_m = 0;
         // steady steps form every global address as (per-task byte base) + zo, one running plane offset in bytes
         const long long zsb = zstride * (long long)sizeof(double);
         long long zo = -(long long)kofs_t * zsb;                            // (ld_m - kofs_t) planes
-        const char *bu_t = reinterpret_cast<const char *>(pu_t), *bf_t = reinterpret_cast<const char *>(pf_t);
         // halo transfer of the same issue; face copies (hmode 3) advance by the face plane stride (running offset zoh)
         const long long fzsb = fzstride * (long long)sizeof(double);
         long long zoh = -(long long)kofs_t * fzsb;
-        const char *bu_h = reinterpret_cast<const char *>(pu_h) + (long long)(kofs_t - kofs_h) * (hmode == 3 ? fzsb : zsb);
-        char *bu_st = reinterpret_cast<char *>(pu_t) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
-        // this lane's own face entry (lanes holding memory column 0 or 7 of row jt), written with the pair
-        const bool face_lane = use_faces && (tp == 0 || tp == 3) && act_t && !(kDbg & 16);
-        double *pf_st = face_lane ? ffaces + (tp == 0 ? 0 : 1) * per_side + ((size_t)I * nz + zb) * a.face_ny + (yb + sy * jt) : nullptr;
-        char *bf_st = reinterpret_cast<char *>(pf_st) - (8 + kPrefetch) * fzsb;
+        const char *bf_t = reinterpret_cast<const char *>(pf_t);
+        const char *bu_t[kNF], *bu_h[kNF];
+        char *bu_st[kNF], *bf_st[kNF];
+#pragma unroll
+        for (int fi = 0; fi < kNF; ++fi) {
+            bu_t[fi] = reinterpret_cast<const char *>(pu_t[fi]);
+            bu_h[fi] = reinterpret_cast<const char *>(pu_h[fi]) + (long long)(kofs_t - kofs_h) * (hmode == 3 ? fzsb : zsb);
+            bu_st[fi] = reinterpret_cast<char *>(pu_t[fi]) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
+            bf_st[fi] = reinterpret_cast<char *>(pf_st[fi]) - (8 + kPrefetch) * fzsb;
+        }
+        const long long pf_ahead = (long long)a.l2_prefetch * zsb;
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
             const int k = ld_m - kofs_t;
             if (kDbg & 4) {
             } else if (kSteady) {
-                cp_async16(sp + cu_t, bu_t + zo);
+#pragma unroll
+                for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, bu_t[fi] + zo);
                 cp_async16(sp + cf_t, bf_t + zo);
+                if (pf_ahead != 0 && k + a.l2_prefetch < ez) {  // planes further ahead: into the L2 only (no shared memory held)
+#pragma unroll
+                    for (int fi = 0; fi < kNF; ++fi) prefetch_l2(bu_t[fi] + zo + pf_ahead);
+                    prefetch_l2(bf_t + zo + pf_ahead);
+                }
             } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
                 const long long z = (long long)min(max(k, klo), khi) * zstride;
-                cp_async16(sp + cu_t, pu_t + z);
+#pragma unroll
+                for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, pu_t[fi] + z);
                 if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + z);
             }
             const int kh = ld_m - kofs_h;
-            if (kDbg & 4) {
-            } else if (kSteady) {  // full brick: every halo lane copies a pair of u (a face entry with face copies)
-                if (hmode == 3) cp_async8(sp + cu_h, bu_h + zoh);
-                else if (hmode != 0) cp_async16(sp + cu_h, bu_h + zo);
-            } else if (hmode == 1) {
-                if (kh >= 0 && kh < ez) cp_async16(sp + cu_h, pu_h + (long long)kh * zstride);
-            } else if (hmode == 2) {
-                if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * zstride);
-            } else if (hmode == 3) {
-                if (kh >= 0 && kh < ez) cp_async8(sp + cu_h, pu_h + (long long)kh * fzstride);
+#pragma unroll
+            for (int fi = 0; fi < kNF; ++fi) {
+                double *sh = sp + fi * kUCells + cu_h;
+                if (kDbg & 4) {
+                } else if (kSteady) {  // full brick: every halo lane copies a pair of u (a face entry with face copies)
+                    if (hmode == 3) cp_async8(sh, bu_h[fi] + zoh);
+                    else if (hmode != 0) cp_async16(sh, bu_h[fi] + zo);
+                } else if (hmode == 1) {
+                    if (kh >= 0 && kh < ez) cp_async16(sh, pu_h[fi] + (long long)kh * zstride);
+                } else if (hmode == 2) {
+                    if (kh >= 0 && kh < ez) cp_async8(sh, pu_h[fi] + (long long)kh * zstride);
+                } else if (hmode == 3) {
+                    if (kh >= 0 && kh < ez) cp_async8(sh, pu_h[fi] + (long long)kh * fzstride);
+                }
             }
             cp_async_commit();
             ++ld_m;
@@ -377,8 +439,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
 
         // ---- compute descriptors
         const int qx = revx ? kBx - 1 - li : li;            // memory column of this lane's sweep column
-        const int cu0 = (j0 + 1) * kURow + qx + 2;          // ring cell of compute column c: cu0 + c * kURow
-        const int cf0 = kUCells + j0 * kBx + qx;
+        const int cu0 = (j0 + 1) * kURow + qx + 2;          // ring cell of compute column c: cu0 + c * kURow (+ fi * kUCells)
+        const int cf0 = kNF * kUCells + j0 * kBx + qx;
         bool act[kNC];
 #pragma unroll
         for (int c = 0; c < kNC; ++c) act[c] = j0 + c < ey;
@@ -390,16 +452,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
 
         cp_async_wait<kPrefetch - 1>();
         __syncwarp();
-        double self[kNC], zm[kNC];
+        // update chain q = fi * kNC + c: node (li, j0 + c) of field fi
+        double self[kNQ], zm[kNQ];
 #pragma unroll
-        for (int c = 0; c < kNC; ++c) {
-            const int k = -li - j0 - c;
-            self[c] = 0.0; zm[c] = 0.0;
-            if (k == 0) {
-                self[c] = U[(ig + j0 + c + 2) * kSlot + cu0 + c * kURow];
-                zm[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
-            } else if (k == -1) {
-                self[c] = U[(ig + j0 + c + 1) * kSlot + cu0 + c * kURow];
+        for (int fi = 0; fi < kNF; ++fi) {
+#pragma unroll
+            for (int c = 0; c < kNC; ++c) {
+                const int k = -li - j0 - c, q = fi * kNC + c, cell = fi * kUCells + cu0 + c * kURow;
+                self[q] = 0.0; zm[q] = 0.0;
+                if (k == 0) {
+                    self[q] = U[(ig + j0 + c + 2) * kSlot + cell];
+                    zm[q] = U[(ig + j0 + c + 1) * kSlot + cell];
+                } else if (k == -1) {
+                    self[q] = U[(ig + j0 + c + 1) * kSlot + cell];
+                }
             }
         }
 
@@ -411,56 +477,74 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             __syncwarp();
 
             const int k0 = l - li - j0;
-            bool go[kNC];
+            bool go[kNQ];
 #pragma unroll
-            for (int c = 0; c < kNC; ++c) go[c] = kSteady || (act[c] && (unsigned)(k0 - c) < (unsigned)ez);
+            for (int fi = 0; fi < kNF; ++fi) {
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) go[fi * kNC + c] = kSteady || (act[c] && (unsigned)(k0 - c) < (unsigned)ez);
+            }
             if (!kSteady && hasbc) {
 #pragma unroll
-                for (int c = 0; c < kNC; ++c)
-                    if (go[c] && ((bcm[k0 - c] >> ((j0 + c) * kBx + li)) & 1ULL)) go[c] = false;
+                for (int fi = 0; fi < kNF; ++fi) {
+#pragma unroll
+                    for (int c = 0; c < kNC; ++c)
+                        if (go[fi * kNC + c] && is_bc(fi, k0 - c, (j0 + c) * kBx + li)) go[fi * kNC + c] = false;
+                }
             }
-            const double *pm = U + om + cu0, *pc = U + oc + cu0, *pp = U + op + cu0;
-            const double *pxm = (xm_prev ? pm : pc) - sx, *pxp = (xp_next ? pp : pc) + sx;
-            double ux[kNC], uy[kNC], uz[kNC], fh[kNC], zp[kNC], nv[kNC];
+            double ux[kNQ], uy[kNQ], uz[kNQ], fh[kNQ], zp[kNQ], nv[kNQ];
 #pragma unroll
-            for (int c = 0; c < kNC; ++c) zp[c] = pp[c * kURow];
+            for (int fi = 0; fi < kNF; ++fi) {
+                const double *pm = U + om + fi * kUCells + cu0, *pc = U + oc + fi * kUCells + cu0, *pp = U + op + fi * kUCells + cu0;
+                const double *pxm = (xm_prev ? pm : pc) - sx, *pxp = (xp_next ? pp : pc) + sx;
 #pragma unroll
-            for (int c = 0; c < kNC; ++c) {
-                ux[c] = dmin2(pxm[c * kURow], pxp[c * kURow]);
-                // the lane's own column supplies two of the y neighbours from registers: row j0+c-1 one plane back is
-                // what the lane wrote (or kept) for its node c-1 in the previous step, row j0+c+1 is zp of node c+1
-                const double ym = c > 0 ? zm[c - 1] : pm[(c - 1) * kURow];
-                const double yp = c + 1 < kNC ? zp[c + 1] : pp[(c + 1) * kURow];
-                uy[c] = dmin2(ym, yp);
-                uz[c] = dmin2(zm[c], zp[c]);
-                fh[c] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
+                for (int c = 0; c < kNC; ++c) zp[fi * kNC + c] = pp[c * kURow];
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) {
+                    const int q = fi * kNC + c;
+                    ux[q] = dmin2(pxm[c * kURow], pxp[c * kURow]);
+                    // the lane's own column supplies two of the y neighbours from registers: row j0+c-1 one plane back is
+                    // what the lane wrote (or kept) for its node c-1 in the previous step, row j0+c+1 is zp of node c+1
+                    const double ym = c > 0 ? zm[q - 1] : pm[(c - 1) * kURow];
+                    const double yp = c + 1 < kNC ? zp[q + 1] : pp[(c + 1) * kURow];
+                    uy[q] = dmin2(ym, yp);
+                    uz[q] = dmin2(zm[q], zp[q]);
+                    fh[q] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
+                }
             }
             if (kDbg & 1) {
 #pragma unroll
-                for (int c = 0; c < kNC; ++c) nv[c] = __dadd_rn(__dadd_rn(ux[c], uy[c]), __dadd_rn(uz[c], fh[c]));
+                for (int q = 0; q < kNQ; ++q) nv[q] = __dadd_rn(__dadd_rn(ux[q], uy[q]), __dadd_rn(uz[q], fh[q]));
             } else {
-                local_solve_xn<kNC>(ux, uy, uz, fh, go, nv);
+                local_solve_xn<kNQ>(ux, uy, uz, fh, go, nv);
             }
 #pragma unroll
-            for (int c = 0; c < kNC; ++c) {
-                const bool upd = go[c] && nv[c] < self[c];  // u = MIN(u, ubar) (fsm3d.f90:477)
-                if (upd) U[oc + cu0 + c * kURow] = nv[c];
-                zm[c] = upd ? nv[c] : self[c];
-                self[c] = zp[c];
+            for (int fi = 0; fi < kNF; ++fi) {
+#pragma unroll
+                for (int c = 0; c < kNC; ++c) {
+                    const int q = fi * kNC + c;
+                    const bool upd = go[q] && nv[q] < self[q];  // u = MIN(u, ubar) (fsm3d.f90:477)
+                    if (upd) U[oc + fi * kUCells + cu0 + c * kURow] = nv[q];
+                    zm[q] = upd ? nv[q] : self[q];
+                    self[q] = zp[q];
+                }
             }
             __syncwarp();
 
-            // slot l - 3 is final: write its pair of this lane back (one 16-byte store)
+            // slot l - 3 is final: write its pair of this lane back (one 16-byte store per field)
             {
                 const int ks = l - 3 - kofs_t;
                 if (!(kDbg & 8) && (kSteady || (act_t && (unsigned)ks < (unsigned)ez))) {
-                    const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + cu_t);
-                    if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st + zo), v);
-                    else __stcg(reinterpret_cast<double2 *>(pu_t + (long long)ks * zstride), v);
-                    if (face_lane) {
-                        const double fv = tp == 0 ? v.x : v.y;
-                        if (kSteady) __stcg(reinterpret_cast<double *>(bf_st + zoh), fv);
-                        else __stcg(pf_st + (long long)ks * fzstride, fv);
+#pragma unroll
+                    for (int fi = 0; fi < kNF; ++fi) {
+                        if (fi > 0 && !st_second) continue;  // the second copy of a single field is never stored
+                        const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + fi * kUCells + cu_t);
+                        if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st[fi] + zo), v);
+                        else __stcg(reinterpret_cast<double2 *>(pu_t[fi] + (long long)ks * zstride), v);
+                        if (face_lane) {
+                            const double fv = tp == 0 ? v.x : v.y;
+                            if (kSteady) __stcg(reinterpret_cast<double *>(bf_st[fi] + zoh), fv);
+                            else __stcg(pf_st[fi] + (long long)ks * fzstride, fv);
+                        }
                     }
                 }
             }
@@ -514,26 +598,33 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
     }
 }
 
+namespace {
+template <bool kPub, int kNF>
+void launch_flavour(const BrickArgs &a, int nsm, cudaStream_t st) {
+    constexpr int kWarps = Cfg<kNF>::kWarps, kWorkers = kPub ? kWarps - 1 : kWarps;
+    const size_t smem = Cfg<kNF>::kWarpSmem * kWarps;
+    const long long ntasks = 8LL * a.nbricks * a.nfields_active;
+    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<kPub, kNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<long long>((ntasks + kWorkers - 1) / kWorkers, nsm);
+    sweep_bricks16_kernel<kPub, kNF><<<grid, kWarps * 32, smem, st>>>(a);
+}
+}  // namespace
+
 void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
     if (a.nfields_active == 0) return;
     if (a.zc < 1 || a.zc > kMaxZc || a.by != kBy || a.nx % kBx != 0) throw CudaError("bricks16: unsupported geometry");
     if (!a.slow_is_fh) throw CudaError("bricks16: expects the slowness premultiplied by h");
-    const size_t smem = kWarpSmem * kWarps;
+    if (a.fields_per_task != 1 && a.fields_per_task != 2) throw CudaError("bricks16: 1 or 2 fields per task");
     int dev = 0, nsm = 0;
     MCEIK_CUDA(cudaGetDevice(&dev));
     MCEIK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    const long long ntasks = 8LL * a.nbricks * a.nfields_active;
-    if (a.publisher) {
-        MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::min<long long>((ntasks + kWarps - 2) / (kWarps - 1), nsm);
-        sweep_bricks16_kernel<true><<<grid, kWarps * 32, smem, st>>>(a);
-    } else {
-        MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = (int)std::min<long long>((ntasks + kWarps - 1) / kWarps, nsm);
-        sweep_bricks16_kernel<false><<<grid, kWarps * 32, smem, st>>>(a);
-    }
+    if (a.fields_per_task == 2) launch_flavour<false, 2>(a, nsm, st);
+    else if (a.publisher) launch_flavour<true, 1>(a, nsm, st);
+    else launch_flavour<false, 1>(a, nsm, st);
     MCEIK_LAUNCH_CHECK();
 }
+
+int bricks16_max_bc_planes() { return kBcMax; }
 
 }  // namespace fsm
 }  // namespace mceik

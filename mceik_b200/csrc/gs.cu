@@ -247,6 +247,8 @@ __global__ void classify_kernel(int nevents, int eb, const int *__restrict__ obs
         }
     }
     ok = __all_sync(0xffffffffu, ok);
+    // a block without any pick, or with more slots than the fast kernel's shared memory holds, takes the general kernel
+    if (maxp == 0 || maxp > kUniformMaxPicks) ok = false;
     if (lane == 0) blk_uniform[b] = ok ? 1 : 0;
 }
 
@@ -473,9 +475,8 @@ void launch_locate(const LocateArgs &a, cudaStream_t st) {
     dim3 grid(a.nlanes, nblocks);
     kern<<<grid, kThreads, smem, st>>>(a);
     MCEIK_LAUNCH_CHECK();
-    if (a.blk_uniform) {
-        const size_t smem_u = locate_uniform_smem_bytes(a.maxpicks);
-        if (smem_u > 100 * 1024) throw CudaError("too many picks per event for the uniform locate kernel");
+    if (a.blk_uniform) {  // blocks classify_kernel marked uniform (at most kUniformMaxPicks slots each)
+        const size_t smem_u = locate_uniform_smem_bytes(std::min(a.maxpicks, kUniformMaxPicks));
         auto ku = locate_uniform_kernel<kEventsPerBlock, kPointsPerThread>;
         MCEIK_CUDA(cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
         ku<<<grid, kThreads, smem_u, st>>>(a);

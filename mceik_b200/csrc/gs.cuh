@@ -11,6 +11,9 @@ namespace mceik {
 namespace gs {
 
 constexpr int kEventsPerBlock = 8;   // events sharing one pass over the tables
+// pick slots of a block the fast (uniform) search kernel holds: 260 B of shared memory per slot, two CTAs per SM
+// (100 KB each); blocks with more slots are searched by the general kernel
+constexpr int kUniformMaxPicks = 392;
 constexpr int kPointsPerThread = 2;  // grid points per thread
 constexpr int kThreads = 256;
 constexpr int kChunk = kThreads * kPointsPerThread;

@@ -82,7 +82,7 @@ inline int build_bc_records(int nx, int ny, int nz, double h, double x0, double 
 // increasing table order is re-laid out over the union of its tables: every event gets one slot per table of the
 // union, "unused" (-1) where it has no pick.  Each event's used picks keep their own order, and unused picks never
 // touch an accumulator, so the results are the same bits.  Other blocks are copied unchanged (general kernel).
-constexpr int kMaxAlignedPicks = 640;  // shared memory of the fast kernel: 260 B per slot
+constexpr int kMaxAlignedPicks = 392;  // = gs::kUniformMaxPicks: a wider union would not fit the fast kernel
 inline void align_event_blocks(int EB, int nevents, const int *optr, const int *tid, const double *tobs, const double *var,
                         std::vector<int> &optr2, std::vector<int> &tid2, std::vector<double> &tobs2,
                         std::vector<double> &var2) {

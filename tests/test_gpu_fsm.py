@@ -94,12 +94,12 @@ def test_both_publication_flavours_of_the_brick_kernel(gpu_ctx, publisher):
     xs, ys, zs = cases.interior_sources(nf, nx, ny, nz, h, seed=4)
     ts = np.zeros(nf)
     ref, its = _oracle_fields(nx, ny, nz, h, slow, fmodel[:6], xs[:6], ys[:6], zs[:6], ts[:6], 1e-6, 20)
-    os.environ["MCEIK_FSM_PUBLISHER"] = publisher
+    gpu_ctx.set_tuning("PUBLISHER", int(publisher)).set_tuning("PAIR_MIN", 0)
     try:
         sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
         u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs)
     finally:
-        os.environ.pop("MCEIK_FSM_PUBLISHER")
+        gpu_ctx.set_tuning("PUBLISHER", -1).set_tuning("PAIR_MIN", 24)
     assert not ferr.any()
     assert np.array_equal(iters[:6], its) and np.array_equal(u[:6], ref)
     # the remaining fields against the other flavour (default for this field count)
@@ -224,6 +224,35 @@ def test_homogeneous_tables(gpu_ctx):
     assert np.array_equal(t, ref)
 
 
+@pytest.mark.parametrize("faces", [0, 1])
+def test_two_fields_per_task(gpu_ctx, faces):
+    """The pair flavour of sweep_bricks16_kernel (two fields of one slowness model walk a brick together, forced here
+    from 2 active fields on): 9 fields over 2 models -- an odd count per model, so one task carries a single field
+    whose second copy is computed and never stored --, several sources in one field, a grid with partial bricks in y
+    and more than one brick along z; with and without the compact x-face copies.  Bit-equal to the oracle."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 40, 28, 300, 200.0
+    n = nx * ny * nz
+    slow = np.stack([cases.checkerboard_slowness(nx, ny, nz, cell=8), cases.random_slowness(n, 5)])
+    nf = 9
+    fmodel = np.array([0, 1, 0, 0, 1, 0, 1, 0, 0], np.int32)
+    xs, ys, zs = cases.interior_sources(nf + 1, nx, ny, nz, h, seed=12)
+    src_ptr = np.array([0, 2] + list(range(3, nf + 2)), np.int32)  # field 0 has two sources
+    ts = np.linspace(0.0, 0.5, nf + 1)
+    gpu_ctx.set_tuning("PAIR_MIN", 2).set_tuning("FACES", faces)
+    try:
+        sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
+        u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, src_ptr=src_ptr)
+    finally:
+        gpu_ctx.set_tuning("PAIR_MIN", 24).set_tuning("FACES", 0)
+    assert not ferr.any()
+    for f in range(nf):
+        a, b = src_ptr[f], src_ptr[f + 1]
+        ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow[fmodel[f]], ts[a:b], xs[a:b], ys[a:b], zs[a:b])
+        assert ierr == 0 and it == iters[f], f"field {f}"
+        assert np.array_equal(u[f], ref), f"field {f}: {np.count_nonzero(u[f] != ref)} nodes differ"
+
+
 def test_solver_building_blocks_selftest(gpu_ctx):
     """sqrt_fast == __dsqrt_rn and the straight-line solver == the reference-ordered solver, bit for
     bit, on 4e8 pseudo-random inputs each (incl. exact squares, ties and u_nan neighbours)."""
@@ -238,7 +267,7 @@ def test_solver_building_blocks_selftest(gpu_ctx):
 def test_full_size_256_all_kernels_agree(gpu_ctx):
     """BASELINE config 3 grid (256^3 checkerboard), 3 fields over the P and S models: the four sweep
     kernels (16-byte bricks, generic bricks, tiles, per-hyperplane cross-check) give bit-identical
-    fields and iteration counts; size-independent properties of the solution hold (stencil nodes keep
+    fields and iteration counts, equal to the oracle's for a P and an S field; size-independent properties of the solution hold (stencil nodes keep
     ts + d*slow, times are finite, non-negative and bounded by the slowest straight ray)."""
     import os
     import torch
@@ -250,8 +279,9 @@ def test_full_size_256_all_kernels_agree(gpu_ctx):
     fmodel = np.array([0, 1, 0], np.int32)
     d_slow = torch.from_numpy(slow).cuda()
     outs = []
-    for algo, env in ((2, {}), (2, {"MCEIK_FSM_NO16": "1"}), (0, {}), (1, {})):
-        os.environ.update(env)
+    for algo, env in ((2, {}), (2, {"NO16": 1}), (0, {}), (1, {})):
+        for k, v in env.items():
+            gpu_ctx.set_tuning(k, v)
         try:
             d_u = torch.empty((3, N), dtype=torch.float64, device="cuda")
             sol = EikonalSolver(gpu_ctx, n, n, n, h, algo=algo)
@@ -261,11 +291,17 @@ def test_full_size_256_all_kernels_agree(gpu_ctx):
             assert not ferr.any()
         finally:
             for k in env:
-                os.environ.pop(k, None)
+                gpu_ctx.set_tuning(k, 0)
     for d_u, iters in outs[1:]:
         assert np.array_equal(iters, outs[0][1])
         assert torch.equal(d_u, outs[0][0])
     u = outs[0][0]
+    # ... and the oracle at this size: one P and one S field, bit for bit, with the oracle's iteration counts
+    O.set_threads(0)
+    for f in (0, 1):
+        ref, ierr, it = O.eikonal_serial(n, n, n, h, slow[fmodel[f]], 0.0, xs[f], ys[f], zs[f], tol=1e-6, maxit=20)
+        assert ierr == 0 and it == outs[0][1][f]
+        assert np.array_equal(u[f].cpu().numpy(), ref), f"field {f}: differs from the oracle at 256^3"
     assert bool(torch.isfinite(u).all()) and float(u.min()) >= 0.0
     diag = np.sqrt(3.0) * (n - 1) * h
     assert float(u[0].max()) <= 1.5 * diag * slow[0].max() and float(u[1].max()) <= 1.5 * diag * slow[1].max()

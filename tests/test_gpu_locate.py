@@ -233,11 +233,11 @@ def test_ragged_sorted_catalog_is_aligned_onto_the_fast_kernel(gpu_ctx):
     loc.set_tables_host(tables, ngrd)
     for job in (2, 1):
         iopt, t0, obj = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
-        os.environ["MCEIK_LOCATE_NO_ALIGN"] = "1"
+        gpu_ctx.set_tuning("LOCATE_NO_ALIGN", 1)
         try:
             iopt_g, t0_g, obj_g = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
         finally:
-            os.environ.pop("MCEIK_LOCATE_NO_ALIGN")
+            gpu_ctx.set_tuning("LOCATE_NO_ALIGN", 0)
         assert np.array_equal(iopt, iopt_g) and np.array_equal(t0, t0_g) and np.array_equal(obj, obj_g)
         for e in range(ne):
             b, en = obs_ptr[e], obs_ptr[e + 1]
@@ -251,6 +251,79 @@ def test_ragged_sorted_catalog_is_aligned_onto_the_fast_kernel(gpu_ctx):
             rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, k, 1, use, stat, ph, np.zeros(k), tori[e:e + 1],
                                                 var[b:en], tc[b:en], np.zeros(ngrd), np.zeros(ngrd), np.zeros(ngrd))
             assert rc == 0 and io[0] == iopt[e] and ob[0] == obj[e] and hy[3] == t0[e], f"event {e}"
+
+
+def _check_events_against_oracle(job, ngrd, tables, obs_ptr, tid, tc, var, tori, iopt, t0, obj):
+    for e in range(len(obs_ptr) - 1):
+        b, en = obs_ptr[e], obs_ptr[e + 1]
+        k = en - b
+        use = (tid[b:en] >= 0).astype(np.int32)
+        if use.sum() == 0:
+            assert iopt[e] == -1, f"event {e}"
+            continue
+        stat = np.where(use == 1, tid[b:en] // 2 + 1, 1).astype(np.int32)
+        ph = np.where(use == 1, tid[b:en] % 2 + 1, 1).astype(np.int32)
+        rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, k, 1, use, stat, ph, np.zeros(k), tori[e:e + 1],
+                                            var[b:en], tc[b:en], np.zeros(ngrd), np.zeros(ngrd), np.zeros(ngrd))
+        assert rc == 0 and io[0] == iopt[e] and ob[0] == obj[e] and hy[3] == t0[e], f"event {e}"
+
+
+@pytest.mark.parametrize("all_empty", [False, True])
+def test_event_blocks_without_picks(gpu_ctx, all_empty):
+    """A trailing block of 8 whose only event has a zero-length pick list (9 events), and a catalogue in which every
+    event is empty: flagged iopt = -1, the other events equal the oracle, no fault in the fast kernel's preload."""
+    from mceik_b200.locate import Locator
+    n, h, tables, _ = _c1_case(nevents=1, n=20, nstat=4)
+    ngrd = n ** 3
+    ntab = tables.shape[0]
+    rng = np.random.default_rng(77)
+    ne = 9
+    obs_ptr, tid, tc, var, tori = [0], [], [], [], rng.uniform(0, 5, ne)
+    for e in range(ne):
+        if not all_empty and e < ne - 1:
+            node = int(rng.integers(0, ngrd))
+            for t in range(ntab):
+                tid.append(t)
+                tc.append(float(tables[t, node]) + tori[e])
+                var.append(0.25)
+        obs_ptr.append(len(tid))
+    obs_ptr = np.array(obs_ptr, np.int32)
+    tid, tc, var = np.array(tid, np.int32), np.array(tc, np.float64), np.array(var, np.float64)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    iopt, t0, obj = loc.locate_host(2, obs_ptr, tid, tc, var, tori)
+    assert iopt[-1] == -1
+    if all_empty:
+        assert np.all(iopt == -1)
+    _check_events_against_oracle(2, ngrd, tables, obs_ptr, tid, tc, var, tori, iopt, t0, obj)
+    gpu_ctx.synchronize()
+
+
+def test_more_picks_than_the_fast_kernel_holds(gpu_ctx):
+    """420 picks per event (the same tables in every event's slot j, so the blocks are uniform, but wider than the
+    392 slots of the fast kernel's shared memory): routed to the general kernel, equal to the oracle."""
+    from mceik_b200.locate import Locator
+    n, h, tables, _ = _c1_case(nevents=1, n=16, nstat=3)
+    ngrd = n ** 3
+    ntab = tables.shape[0]
+    rng = np.random.default_rng(78)
+    ne, npk = 10, 420
+    obs_ptr, tid, tc, var, tori = [0], [], [], [], rng.uniform(0, 5, ne)
+    for e in range(ne):
+        node = int(rng.integers(0, ngrd))
+        for j in range(npk):
+            t = j % ntab
+            tid.append(t if rng.random() > 0.1 else -1)
+            tc.append(float(tables[t, node]) + tori[e] + rng.normal(0, 0.05))
+            var.append(float(rng.choice([0.1, 0.25, 0.5])))
+        obs_ptr.append(len(tid))
+    obs_ptr = np.array(obs_ptr, np.int32)
+    tid, tc, var = np.array(tid, np.int32), np.array(tc, np.float64), np.array(var, np.float64)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    for job in (2, 1):
+        iopt, t0, obj = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
+        _check_events_against_oracle(job, ngrd, tables, obs_ptr, tid, tc, var, tori, iopt, t0, obj)
 
 
 def test_catalog_struct_entry(gpu_ctx):

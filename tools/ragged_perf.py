@@ -22,7 +22,7 @@ for e in range(ne):
     obs_ptr.append(len(tid))
 obs_ptr, tid, tc, var = np.array(obs_ptr, np.int32), np.array(tid, np.int32), np.array(tc), np.array(var)
 for mode in ("aligned", "general"):
-    if mode == "general": os.environ["MCEIK_LOCATE_NO_ALIGN"] = "1"
+    ctx.set_tuning("LOCATE_NO_ALIGN", 1 if mode == "general" else 0)
     for rep in range(3):
         t = time.time(); iopt, t0, obj = loc.locate_host(2, obs_ptr, tid, tc, var, tori); dt = time.time() - t
     print(mode, f"{ne/dt:.1f} events/s", int(iopt.sum()))
