@@ -47,7 +47,7 @@ struct mceik_ctx {
     // device time of the sweep kernel launches of the last solve (CUDA events on ctx->stream)
     double last_sweep_ms = 0.0;
     int last_sweep_launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fin = nullptr;
     // mceik_fsm_solve_batched_host with pinned output: a converged field is copied back on copy_stream while
     // the remaining fields keep iterating (early_u = host destination, early_done[f] = already on its way)
     cudaStream_t copy_stream = nullptr;
@@ -65,14 +65,13 @@ struct mceik_ctx {
         int publisher = -1;   // 0 / 1: force one publication flavour
         int no_stagger = 0;   // 1: one field group in the ticket order
         int pair_min = 24;    // two fields per task from this many active fields on (0 = never)
-        int faces = 0;        // 1: compact x-face copies (BrickArgs::faces)
-        int l2pf = 0;         // planes prefetched into the L2 ahead of the ring (0 = off)
+        int natural = 0;      // 1: bricks16 works on the caller's [z][y][x] layout instead of the blocked one
         int batch = 0;        // sequential field batches (experiment)
         int trace = 0, stats = 0, debug = 0;
         int locate_no_align = 0;  // 1: keep ragged event blocks on the general search kernel (MCEIK_LOCATE_NO_ALIGN)
     } tune;
     // eikonal workspaces
-    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_faces;
+    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_ub, ws_u0b;
     // locator state
     const float *d_tables = nullptr;
     DevBuf own_tables;
@@ -88,14 +87,14 @@ int *tuning_slot(mceik_ctx *c, const char *key) {
     struct { const char *name; int *p; } const tab[] = {
         {"ZC", &c->tune.zc}, {"BY", &c->tune.by}, {"NO16", &c->tune.no16}, {"PUBLISH", &c->tune.publish},
         {"PUBLISHER", &c->tune.publisher}, {"NO_STAGGER", &c->tune.no_stagger}, {"PAIR_MIN", &c->tune.pair_min},
-        {"FACES", &c->tune.faces}, {"L2PF", &c->tune.l2pf}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
+        {"NATURAL", &c->tune.natural}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
         {"STATS", &c->tune.stats}, {"DEBUG", &c->tune.debug}, {"LOCATE_NO_ALIGN", &c->tune.locate_no_align}};
     for (const auto &e : tab)
         if (strcmp(e.name, key) == 0) return e.p;
     return nullptr;
 }
 void tuning_from_env(mceik_ctx *c) {
-    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "PAIR_MIN", "FACES", "L2PF", "BATCH", "TRACE",
+    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "PAIR_MIN", "NATURAL", "BATCH", "TRACE",
                           "STATS", "DEBUG"}) {
         const std::string name = std::string("MCEIK_FSM_") + k;
         if (const char *e = getenv(name.c_str())) *tuning_slot(c, k) = atoi(e);
@@ -157,6 +156,10 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         set_error("mceik_fsm_solve_batched: ldtab < nx*ny*nz");
         return -1;
     }
+    if ((reinterpret_cast<uintptr_t>(d_u) | reinterpret_cast<uintptr_t>(d_slow)) % 16 != 0) {
+        set_error("mceik_fsm_solve_batched: d_u and d_slow must be 16-byte aligned (128-bit accesses)");
+        return -1;
+    }
     for (int f = 0; f < nfields; ++f)
         if (field_model[f] < 0 || field_model[f] >= nmodels) {
             set_error("mceik_fsm_solve_batched: field_model[%d] out of range", f);
@@ -172,10 +175,10 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     if (!ctx->ev0) {
         MCEIK_CUDA(cudaEventCreate(&ctx->ev0));
         MCEIK_CUDA(cudaEventCreate(&ctx->ev1));
+        MCEIK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming));
     }
 
     if (!d_u) d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * nfields));
-    double *d_u0 = static_cast<double *>(ctx->ws_u0.ensure(sizeof(double) * N * nfields));
     ctx->plan.build(nx, ny, nz, st);
     const fsm::TilePlan &pl = ctx->plan;
     const bool bricks = ctx->fsm_algo == MCEIK_FSM_ALGO_BRICKS;
@@ -259,21 +262,32 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         for (auto &kv : planes)
             if ((int)kv.second.size() > fsm::bricks16_max_bc_planes()) bricks16 = false;  // -> generic brick kernel
     }
+    // bricks16 works on its own blocked copy of the fields (BrickArgs::blocked: 512 contiguous bytes per brick plane
+    // + x-face copies; the [z][y][x] walk tops out at ~4.4 TB/s of DRAM traffic in 64-byte pieces, the blocked one at
+    // ~6.1 TB/s, tools/stream_bench.cu) and reads slow*h, formed once per solve instead of once per node visit.
+    // Converged fields are converted back into d_u.
+    const bool blocked = bricks16 && !ctx->tune.natural;
+    const size_t Nb = blocked ? fsm::blocked_field_doubles(nx, ny, nz) : N;  // doubles per field the iterations work on
     const double *d_fh = nullptr;
-    if (bricks16) {
-        double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * N * nmodels));
-        fsm::launch_scale_slowness(N * nmodels, g->h, d_slow, fh, st);
+    double *d_w = d_u, *d_w0 = nullptr;  // fields / start-of-iteration copy the sweeps and the convergence test use
+    if (blocked) {
+        double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * fsm::blocked_slowness_doubles(nx, ny, nz) * nmodels));
+        fsm::launch_scale_slowness_blocked(nx, ny, nz, nmodels, g->h, d_slow, fh, st);
         d_fh = fh;
+        d_w = static_cast<double *>(ctx->ws_ub.ensure(sizeof(double) * Nb * nfields));
+        d_w0 = static_cast<double *>(ctx->ws_u0b.ensure(sizeof(double) * Nb * nfields));
+        fsm::launch_block_fields(nx, ny, nz, nfields, d_u, d_w, st);
+    } else {
+        if (bricks16) {
+            double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * N * nmodels));
+            fsm::launch_scale_slowness(N * nmodels, g->h, d_slow, fh, st);
+            d_fh = fh;
+        }
+        d_w0 = static_cast<double *>(ctx->ws_u0.ensure(sizeof(double) * N * nfields));
     }
-    // compact x-face copies of every field (BrickArgs::faces), filled from u once the boundary conditions are in
-    double *d_faces = nullptr;
-    const int face_ny = (ny + 7) / 8 * 8;
-    if (bricks16 && ctx->tune.faces) {  // measured slower so far (8-byte face stores), profiles/kernel_evolution_r2.md
-        d_faces = static_cast<double *>(ctx->ws_faces.ensure(sizeof(double) * 2 * (size_t)(nx / 8) * nz * face_ny * nfields));
-        fsm::launch_extract_faces(nx, ny, nz, face_ny, nfields, nullptr, d_u, d_faces, st);
-    }
+    double *d_u0 = d_w0;
     if (bricks)  // u0 = u before the first iteration (fsm3d.f90:60); refreshed by the convergence kernel
-        MCEIK_CUDA(cudaMemcpyAsync(d_u0, d_u, sizeof(double) * N * nfields, cudaMemcpyDeviceToDevice, st));
+        MCEIK_CUDA(cudaMemcpyAsync(d_w0, d_w, sizeof(double) * Nb * nfields, cudaMemcpyDeviceToDevice, st));
     uint8_t *d_lupd = nullptr;
     if (ctx->fsm_algo == MCEIK_FSM_ALGO_LEVELS) {
         d_lupd = static_cast<uint8_t *>(ctx->ws_lupd.ensure(N * nfields));
@@ -315,14 +329,12 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             if (ctx->tune.publish > 0) a.publish = ctx->tune.publish;
             a.h = g->h;
             a.active = d_units; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
-            a.u = d_u;
+            a.u = d_w; a.blocked = blocked ? 1 : 0;
             a.brick_order = ctx->bplan.brick_order.as<int>();
             a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);
             a.done = reinterpret_cast<int *>(ctrl + c_done);
             a.bc_ptr = d_bcptr; a.bc_node = d_recn;
-            a.faces = d_faces; a.face_ny = face_ny;
-            a.l2_prefetch = ctx->tune.l2pf;
             a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0; a.batch = 0;
             // few active fields: a publisher warp per CTA takes the release fences off the sweeping warps (+8-12 % up to
             // 11 fields, +1 % at 16, nothing beyond; profiles/kernel_evolution_r1.md)
@@ -348,7 +360,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             else fsm::launch_iteration_bricks(a, st);
             MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
             ctx->last_sweep_launches += 1;
-            fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
+            fsm::launch_convergence(Nb, (int)active.size(), d_active, g->tol, d_w, d_w0, d_nonconv, st);
         } else {
             // group the active fields by slowness model, up to kMaxSlots per CTA
             std::map<int, std::vector<int>> by_model;
@@ -406,10 +418,24 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             it[f] = k;
             if (h_nonconv[f] != 0) still.push_back(f);  // lconv /= nxyz -> next iteration (fsm3d.f90:95)
         }
-        if (ctx->early_u) {  // the stream is idle here (synchronised above), so a field that just converged is final
+        std::vector<int> finished;  // fields that have just converged (or run out of iterations): final
+        {
             size_t j = 0;
             for (int f : active) {
-                if (j < still.size() && still[j] == f) { ++j; continue; }
+                if (k < g->maxit && j < still.size() && still[j] == f) { ++j; continue; }
+                finished.push_back(f);
+            }
+        }
+        if (blocked && !finished.empty()) {  // back into the caller's layout
+            const int *d_fin = upload(ctx->ws_meta, o_units, finished, st);
+            fsm::launch_unblock_fields(nx, ny, nz, (int)finished.size(), d_fin, d_w, d_u, st);
+        }
+        if (ctx->early_u && !finished.empty()) {  // copy them back while the others keep iterating
+            if (blocked) {
+                MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, st));
+                MCEIK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fin, 0));
+            }  // else: the stream is idle here (synchronised above) and d_u[f] is final
+            for (int f : finished) {
                 MCEIK_CUDA(cudaMemcpyAsync(ctx->early_u + (size_t)f * N, d_u + (size_t)f * N, sizeof(double) * N,
                                            cudaMemcpyDeviceToHost, ctx->copy_stream));
                 ctx->early_done[f] = 1;
@@ -547,11 +573,12 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         cudaStreamSynchronize(c->stream);
         c->plan.release();
         c->bplan.release();
-        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh, &c->ws_faces,
+        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh, &c->ws_ub, &c->ws_u0b,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
+        if (c->ev_fin) cudaEventDestroy(c->ev_fin);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     } catch (...) {
@@ -653,10 +680,14 @@ int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int
                                field_ierr);
         } catch (...) {
             ctx->early_u = nullptr;
+            if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // no copy into the caller's buffer may outlive the call
             throw;
         }
         ctx->early_u = nullptr;
-        if (rc < 0) return rc;
+        if (rc < 0) {
+            if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+            return rc;
+        }
         if (u && pinned) {
             for (int f = 0; f < nfields; ++f)  // fields that stopped at maxit or failed their boundary conditions
                 if (!ctx->early_done[f])

@@ -477,29 +477,83 @@ void launch_scale_slowness(size_t n, double h, const double *d_slow, double *d_o
     MCEIK_LAUNCH_CHECK();
 }
 
-__global__ void extract_faces_kernel(int nx, int ny, int nz, int face_ny, const int *__restrict__ fields,
-                                     const double *__restrict__ u, double *__restrict__ faces) {
-    const int f = fields ? fields[blockIdx.y] : blockIdx.y;
-    const int nbx = nx / 8;
-    const size_t nxy = (size_t)nx * ny, N = nxy * nz, per_side = (size_t)nbx * nz * face_ny;
-    const size_t total = 2 * (size_t)nbx * nz * ny, stride = (size_t)gridDim.x * blockDim.x;
+// ---- blocked layout of the bricks16 kernel: [field][brick column][z][80] (fsm.cuh, BrickArgs::blocked)
+constexpr int kRecU = 80, kRecS = 64;
+size_t blocked_field_doubles(int nx, int ny, int nz) { return (size_t)(nx / 8) * ((ny + 7) / 8) * nz * kRecU; }
+size_t blocked_slowness_doubles(int nx, int ny, int nz) { return (size_t)(nx / 8) * ((ny + 7) / 8) * nz * kRecS; }
+
+// one thread per record entry e in [0, 80): 0..63 node (j, i), 64..71 copy of column 0, 72..79 copy of column 7
+__global__ void block_fields_kernel(int nx, int ny, int nz, const double *__restrict__ u, double *__restrict__ ub) {
+    const int nbx = nx / 8, nby = (ny + 7) / 8;
+    const size_t nxy = (size_t)nx * ny, N = nxy * nz, nrec = (size_t)nbx * nby * nz;
+    const size_t total = nrec * kRecU, stride = (size_t)gridDim.x * blockDim.x;
+    const double *uf = u + (size_t)blockIdx.y * N;
+    double *ubf = ub + (size_t)blockIdx.y * total;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        // t -> (z, y, I, side): consecutive threads read the two face columns of consecutive bricks of one grid row
-        const int side = (int)(t & 1);
-        const int I = (int)((t >> 1) % nbx);
-        const size_t r = (t >> 1) / nbx;
-        const int y = (int)(r % ny), z = (int)(r / ny);
-        faces[(size_t)f * 2 * per_side + side * per_side + ((size_t)I * nz + z) * face_ny + y] =
-            u[(size_t)f * N + (size_t)z * nxy + (size_t)y * nx + 8 * I + 7 * side];
+        const int e = (int)(t % kRecU);
+        const size_t rec = t / kRecU;
+        const int z = (int)(rec % nz);
+        const size_t colid = rec / nz;
+        const int I = (int)(colid % nbx), J = (int)(colid / nbx);
+        const int j = e < 64 ? e >> 3 : (e - 64) & 7, i = e < 64 ? e & 7 : (e < 72 ? 0 : 7);
+        const int y = J * 8 + j;
+        ubf[t] = y < ny ? uf[(size_t)z * nxy + (size_t)y * nx + I * 8 + i] : DBL_MAX;
     }
 }
 
-void launch_extract_faces(int nx, int ny, int nz, int face_ny, int nfields, const int *d_fields, const double *d_u,
-                          double *d_faces, cudaStream_t st) {
+void launch_block_fields(int nx, int ny, int nz, int nfields, const double *d_u, double *d_ub, cudaStream_t st) {
     if (nfields == 0) return;
-    const size_t total = 2 * (size_t)(nx / 8) * nz * ny;
-    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 148 * 4), nfields);
-    extract_faces_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, face_ny, d_fields, d_u, d_faces);
+    const size_t total = blocked_field_doubles(nx, ny, nz);
+    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), nfields);
+    block_fields_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, d_u, d_ub);
+    MCEIK_LAUNCH_CHECK();
+}
+
+__global__ void unblock_fields_kernel(int nx, int ny, int nz, const int *__restrict__ fields, const double *__restrict__ ub,
+                                      double *__restrict__ u) {
+    const int f = fields ? fields[blockIdx.y] : blockIdx.y;
+    const int nbx = nx / 8, nby = (ny + 7) / 8;
+    const size_t nxy = (size_t)nx * ny, N = nxy * nz, stride = (size_t)gridDim.x * blockDim.x;
+    const double *ubf = ub + (size_t)f * ((size_t)nbx * nby * nz * kRecU);
+    double *uf = u + (size_t)f * N;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += stride) {  // t = node: coalesced writes
+        const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / nxy);
+        uf[t] = ubf[(((size_t)(y >> 3) * nbx + (x >> 3)) * nz + z) * kRecU + (y & 7) * 8 + (x & 7)];
+    }
+}
+
+void launch_unblock_fields(int nx, int ny, int nz, int nfields, const int *d_fields, const double *d_ub, double *d_u,
+                           cudaStream_t st) {
+    if (nfields == 0) return;
+    const size_t N = (size_t)nx * ny * nz;
+    dim3 grid((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), nfields);
+    unblock_fields_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, d_fields, d_ub, d_u);
+    MCEIK_LAUNCH_CHECK();
+}
+
+__global__ void scale_slowness_blocked_kernel(int nx, int ny, int nz, double h, const double *__restrict__ slow,
+                                              double *__restrict__ out) {
+    const int nbx = nx / 8, nby = (ny + 7) / 8;
+    const size_t nxy = (size_t)nx * ny, N = nxy * nz, total = (size_t)nbx * nby * nz * kRecS;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const double *sf = slow + (size_t)blockIdx.y * N;
+    double *of = out + (size_t)blockIdx.y * total;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int e = (int)(t % kRecS);
+        const size_t rec = t / kRecS;
+        const int z = (int)(rec % nz);
+        const size_t colid = rec / nz;
+        const int I = (int)(colid % nbx), J = (int)(colid / nbx), y = J * 8 + (e >> 3);
+        of[t] = y < ny ? __dmul_rn(sf[(size_t)z * nxy + (size_t)y * nx + I * 8 + (e & 7)], h) : 1.0;
+    }
+}
+
+void launch_scale_slowness_blocked(int nx, int ny, int nz, int nmodels, double h, const double *d_slow, double *d_out,
+                                   cudaStream_t st) {
+    if (nmodels == 0) return;
+    const size_t total = blocked_slowness_doubles(nx, ny, nz);
+    dim3 grid((unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), nmodels);
+    scale_slowness_blocked_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, h, d_slow, d_out);
     MCEIK_LAUNCH_CHECK();
 }
 

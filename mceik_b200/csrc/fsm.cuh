@@ -94,13 +94,11 @@ struct BrickArgs {
     // (sweep, level) = divmod(V, nblevels) of group 0 and divmod(V - stagger, nblevels) of group 1.
     const long long *vptr;        // [8 * nblevels + stagger + 1] tickets before virtual level V
     int nf0, stagger;             // group 0 = active[0, nf0), group 1 = active[nf0, nfields_active)
-    // bricks16: compact copies of every brick's two x-face columns, faces[field][side][I][z][y] (side 0 = column 8I,
-    // side 1 = column 8I+7; y padded to face_ny), always equal to u at those nodes.  A brick takes its x-halo columns
-    // from its neighbours' copies (64 contiguous bytes per plane and side instead of 8 separate sectors of u) and keeps
-    // its own copies up to date when it writes u back.  nullptr = halo columns are read from u.
-    double *faces;
-    int face_ny;
-    int l2_prefetch;              // bricks16: planes ahead of the ring's own loads that are prefetched into the L2 (0 = off)
+    // bricks16, blocked layout: u is [field][brick column J * nbx + I][z][80] -- the 8 x 8 nodes of one brick plane
+    // (row-major, 512 contiguous bytes) followed by copies of its columns 0 and 7 (8 + 8 values), which the x
+    // neighbours read as their halo instead of 8 separate sectors of u; slow is [model][brick column][z][64].  Rows
+    // beyond ny hold u_nan.  launch_block_fields / launch_unblock_fields convert from / to the [z][y][x] layout.
+    int blocked;
     int batch;                    // bricks16 experiment (MCEIK_FSM_BATCH): > 0 = fields run in sequential batches of this size
     int publisher;                // bricks16: 1 = the last warp of every CTA publishes progress for the others
     const int *bc_ptr;            // [nfields+1] CSR into bc_node
@@ -163,9 +161,16 @@ void launch_convergence(size_t n, int nfields, const int *d_active_fields, doubl
                         double *d_u0, unsigned long long *d_nonconv, cudaStream_t st);
 void launch_mark_bcs(int nrec, const int *d_rec_field, const int *d_rec_node, size_t n, uint8_t *d_lupd,
                      cudaStream_t st);
-// faces[f][side][I][z][y] = u[f][z][y][8I + 7*side] for the listed fields (BrickArgs::faces)
-void launch_extract_faces(int nx, int ny, int nz, int face_ny, int nfields, const int *d_fields, const double *d_u,
-                          double *d_faces, cudaStream_t st);
+// Blocked layout of the bricks16 kernel (BrickArgs::blocked).  block: d_ub[f] = records of d_u[f] for every field
+// (u_nan in rows beyond ny); unblock: d_u[f] = nodes of d_ub[f] for the listed fields (d_fields == nullptr: all).
+size_t blocked_field_doubles(int nx, int ny, int nz);
+size_t blocked_slowness_doubles(int nx, int ny, int nz);
+void launch_block_fields(int nx, int ny, int nz, int nfields, const double *d_u, double *d_ub, cudaStream_t st);
+void launch_unblock_fields(int nx, int ny, int nz, int nfields, const int *d_fields, const double *d_ub, double *d_u,
+                           cudaStream_t st);
+// d_out[model][brick column][z][64] = d_slow[model][z][y][x] * h (1.0 in rows beyond ny)
+void launch_scale_slowness_blocked(int nx, int ny, int nz, int nmodels, double h, const double *d_slow, double *d_out,
+                                   cudaStream_t st);
 // fp64 field -> fp32 table (fsm3d.f90:1870-1872, homog.c:624-635)
 void launch_pack_tables(int nfields, size_t n, size_t ldtab, const double *d_u, float *d_tables,
                         cudaStream_t st);

@@ -44,11 +44,17 @@ constexpr int kDbg = MCEIK_DBG;
 constexpr int kBx = 8, kBy = 8, kNC = 2;
 constexpr int kPrefetch = 2;
 constexpr int kRing = 9 + kPrefetch;
-constexpr int kURow = 12;                          // row: [pad(-2) halo(-1) | 0..7 | halo(8) pad(9)]
-constexpr int kUCells = kURow * (kBy + 2);
+// ring cell of node (row j, memory column q), j in [-1, By], q in [-1, Bx]: (j + 1) * kURow + q + 2 -- a row is 10 cells
+// wide and its column -1 shares the stride with the previous row's unused 10th cell; pairs of columns start on even
+// cells (16-byte transfers), and the stride keeps the lanes of a 64-bit access on different banks
+constexpr int kURow = 10;
+constexpr int kUCells = kURow * (kBy + 2) + 2;     // 102
+constexpr int kFRow = 10;                          // slowness tile: row stride (8 used)
+constexpr int kFCells = kFRow * kBy;
 constexpr int kMaxZc = 256;
 constexpr int kProgShift = 12;
 constexpr int kLead = kBy + 3;
+constexpr int kRec = kBx * kBy + 2 * kBy;          // blocked layout: doubles per brick plane (64 nodes + the two x-face copies)
 constexpr int kBcMax = 16;                         // planes of one brick that hold boundary-condition nodes of one field
 // kNF fields of one slowness model walk the same brick in one task (template parameter of the kernel): their ring
 // slots sit side by side ([field 0 rows][field 1 rows][slowness]), the slowness tile is loaded once, every address
@@ -56,9 +62,11 @@ constexpr int kBcMax = 16;                         // planes of one brick that h
 template <int kNF>
 struct Cfg {
     static constexpr int kWarps = kNF == 2 ? 8 : 12;
-    static constexpr int kSlot = kNF * kUCells + kBx * kBy;  // 184 / 304 doubles, 16-byte aligned
+    static constexpr int kSlot = kNF * kUCells + kFCells;  // 182 / 284 doubles, 16-byte aligned
     static constexpr int kBcBytes = kNF * kBcMax * 16;       // [kNF][kBcMax] masks (8 B), then [kNF][kBcMax] planes (4 B, padded)
-    static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot) + kBcBytes;
+    static constexpr int kFaceCells = kNF * 2 * kBy * kBy;   // blocked layout: [field][x side][plane & 7][row] face values on
+                                                             // their way to the brick records (see BrickArgs::blocked)
+    static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot + kFaceCells) + kBcBytes;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -69,7 +77,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void *g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -163,7 +170,8 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         }
     };
     double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
-    unsigned long long *bc_mask = reinterpret_cast<unsigned long long *>(U + kRing * kSlot);  // [kNF][kBcMax]
+    double *FB = U + kRing * kSlot;                                                            // [kNF][2][8][8]
+    unsigned long long *bc_mask = reinterpret_cast<unsigned long long *>(FB + Cfg<kNF>::kFaceCells);  // [kNF][kBcMax]
     int *bc_plane = reinterpret_cast<int *>(bc_mask + kNF * kBcMax);                           // [kNF][kBcMax], -1 = free
 
     const int nx = a.nx, ny = a.ny, nz = a.nz;
@@ -248,7 +256,9 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
                 // lane 0 watches the upwind x neighbour, lane 1 the upwind y neighbour.  A slot's y-halo row is the
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
-                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? kBy - 2 : 0);
+                // Blocked layout: the x-halo comes from the neighbour's face copies, written one whole plane at a
+                // time 14 steps after the plane was entered: x needs 1 step MORE lead than y.
+                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? -1 : kBy - 2) : 0);
                 seen = max(seen, ahead);
                 if (seen < need)
                     while ((seen = ld_acquire_gpu(up_ptr)) < need) __nanosleep(200);
@@ -267,10 +277,14 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         const int ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
         const int yb = revy ? y_hi : y_lo, zb = revz ? z_hi : z_lo;
         const int sx = revx ? -1 : 1, sy = revy ? -1 : 1, sz = revz ? -1 : 1;
+        // blocked layout (BrickArgs::blocked): a field is [brick column][z][80], the slowness [brick column][z][64]
+        const bool blocked = a.blocked != 0;
+        const size_t ncol = (size_t)a.nbx * a.nby;
+        const size_t fstride = blocked ? ncol * nz * kRec : N, sstride = blocked ? ncol * nz * (kBx * kBy) : N;
         double *ufs[kNF];
 #pragma unroll
-        for (int fi = 0; fi < kNF; ++fi) ufs[fi] = a.u + (size_t)fld[fi] * N;
-        const double *sl = a.slow + (size_t)__ldg(a.field_model + f) * N;
+        for (int fi = 0; fi < kNF; ++fi) ufs[fi] = a.u + (size_t)fld[fi] * fstride;
+        const double *sl = a.slow + (size_t)__ldg(a.field_model + f) * sstride;
 
         // ---- boundary-condition nodes inside the brick: per field a short list of (plane, 64-bit mask) with
         // bit = j * 8 + i in sweep coordinates (at most kBcMax planes per field and brick; the host checks)
@@ -314,43 +328,48 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         };
 
         // ---- transfer descriptors of this lane (all per task): interior pair, slowness pair, halo pair
-        const long long zstride = (long long)sz * (long long)nxy;
+        // plane strides of a field and of the slowness (blocked: one record each)
+        const long long zstride = blocked ? (long long)sz * kRec : (long long)sz * (long long)nxy;
+        const long long szstride = blocked ? (long long)sz * (kBx * kBy) : zstride;
         const int klo = (zb - sz < 0 || zb - sz > nz - 1) ? 0 : -1;
         const int khi = (zb + sz * ez < 0 || zb + sz * ez > nz - 1) ? ez - 1 : ez;
+        const size_t col = (size_t)J * a.nbx + I;  // brick column (blocked records are indexed by column and plane)
         // interior pair (2tp, 2tp+1) of row jt: sweep index of its first node decides the x-group
         const int gi = xgroup(revx ? kBx - 1 - 2 * tp : 2 * tp);
         const int kofs_t = gi + jt + 2;
-        const size_t rowt = (size_t)zb * nxy + (size_t)min(max(yb + sy * jt, 0), ny - 1) * nx + x_lo + 2 * tp;
-        const double *pf_t = sl + rowt;
+        // rows beyond ey of a partial brick are transferred too: row ey is the clamped boundary row or, in a sweep
+        // against y, the nearest row of the next brick (it serves as the last row's halo)
+        const int yt = min(max(yb + sy * jt, 0), ny - 1);
+        const size_t colt = (size_t)(yt / kBy) * a.nbx + I;
+        const size_t rowt = blocked ? (colt * nz + zb) * kRec + (size_t)(yt % kBy) * kBx + 2 * tp
+                                    : (size_t)zb * nxy + (size_t)yt * nx + x_lo + 2 * tp;
+        const double *pf_t = sl + (blocked ? (colt * nz + zb) * (kBx * kBy) + (size_t)(yt % kBy) * kBx + 2 * tp : rowt);
         // ring cells: field fi's rows start at fi * kUCells, the slowness tile follows the last field
-        const int cu_t = (jt + 1) * kURow + 2 * tp + 2, cf_t = kNF * kUCells + jt * kBx + 2 * tp;
+        const int cu_t = (jt + 1) * kURow + 2 * tp + 2, cf_t = kNF * kUCells + jt * kFRow + 2 * tp;
         const bool act_t = jt < ey;
-        // halo pair of lanes 0..23: 0-7 left x pair (q = -2,-1) of row h; 8-15 right x pair (q = 8,9) of row
-        // h-8; 16-19 row j = -1, pair h-16; 20-23 row j = By, pair h-20.  hmode: 0 none, 1 pair copy,
-        // 2 clamped single column (brick on the grid's x face: the halo repeats the boundary column)
+        // halo transfer of lanes 0..23: 0-7 left x halo of row h; 8-15 right x halo of row h-8; 16-19 row j = -1, pair
+        // h-16; 20-23 row j = By, pair h-20.  hmode: 0 none, 1 pair copy (y rows), 2 one value (x columns): the
+        // neighbour's column -- blocked: the entry of its face copy -- or, for a brick on the grid's x face, the
+        // boundary column itself (the halo repeats the boundary node, fsm3d.f90:495-499)
         int hmode = 0, kofs_h = 0, cu_h = 0;
-        size_t offh = 0;  // offset of the halo transfer's source inside a field (or inside a field's face copies)
-        // x-face copies (BrickArgs::faces): hmode 3 = one 8-byte copy per row from the neighbour's face column copy
-        // (the brick's own copy where the halo is the clamped boundary column, fsm3d.f90:495-499)
-        const bool use_faces = a.faces != nullptr;
-        const size_t per_side = (size_t)a.nbx * nz * a.face_ny;
-        const long long fzstride = (long long)sz * a.face_ny;
+        size_t offh = 0;  // offset of the halo transfer's source inside a field
         if (lane < 16) {
             const bool left = lane < 8;
             const int hj = lane & 7;
             const int ih = left ? (revx ? kBx : -1) : (revx ? -1 : kBx);  // sweep index of the needed halo column
             kofs_h = xgroup(ih) + hj + 2;
-            const size_t row = (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx;
-            const bool inside = left ? x_lo >= 2 : x_lo + kBx + 1 <= nx - 1;
+            const int yh = min(max(yb + sy * hj, 0), ny - 1);
+            const size_t row = (size_t)zb * nxy + (size_t)yh * nx;
+            const bool in_f = left ? I > 0 : I < a.nbx - 1;  // else the halo is the clamped boundary column itself
             if (hj < ey) {
-                if (use_faces && !(kDbg & 32)) {
-                    const bool in_f = left ? I > 0 : I < a.nbx - 1;
-                    const int side = left ? (in_f ? 1 : 0) : (in_f ? 0 : 1);
-                    const int In = left ? (in_f ? I - 1 : I) : (in_f ? I + 1 : I);
-                    hmode = 3; cu_h = (hj + 1) * kURow + (left ? 1 : 10);
-                    offh = side * per_side + ((size_t)In * nz + zb) * a.face_ny + min(max(yb + sy * hj, 0), ny - 1);
-                } else if (inside) { hmode = 1; cu_h = (hj + 1) * kURow + (left ? 0 : 10); offh = row + (left ? x_lo - 2 : x_lo + kBx); }
-                else { hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10); offh = row + (left ? x_lo : x_lo + kBx - 1); }
+                hmode = 2; cu_h = (hj + 1) * kURow + (left ? 1 : 10);
+                if (blocked) {
+                    const int side = left ? (in_f ? 1 : 0) : (in_f ? 0 : 1);  // 0 = copy of column 0, 1 = of column 7
+                    const size_t cn = left ? (in_f ? col - 1 : col) : (in_f ? col + 1 : col);
+                    offh = (cn * nz + zb) * kRec + kBx * kBy + side * kBy + (yh - y_lo);
+                } else {
+                    offh = row + (left ? (in_f ? x_lo - 1 : x_lo) : (in_f ? x_lo + kBx : x_lo + kBx - 1));
+                }
             }
         } else if (lane < 24) {
             const bool low = lane < 20;
@@ -360,39 +379,51 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             kofs_h = gh + hj + 2;
             hmode = 1;
             cu_h = (hj + 1) * kURow + 2 * hp + 2;
-            offh = (size_t)zb * nxy + (size_t)min(max(yb + sy * hj, 0), ny - 1) * nx + x_lo + 2 * hp;
+            const int yh = min(max(yb + sy * hj, 0), ny - 1);  // the neighbour brick's nearest row, or the clamped boundary row
+            offh = blocked ? (((size_t)(yh / kBy) * a.nbx + I) * nz + zb) * kRec + (size_t)(yh % kBy) * kBx + 2 * hp
+                           : (size_t)zb * nxy + (size_t)yh * nx + x_lo + 2 * hp;
+        }
+        // blocked: values of memory columns 0 and 7 go to the face staging FB[field][side][plane & 7][row] when their
+        // pair is written back, and a whole plane of a side (64 contiguous bytes of the record) is stored once its
+        // 8 rows are in: 13 steps after the plane was entered for the side of sweep column 0, 14 for sweep column 7
+        const bool face_lane = blocked && (tp == 0 || tp == 3) && act_t;
+        const int fb_t = (tp == 0 ? 0 : 1) * (kBy * kBy) + (yt - y_lo);       // + (plane & 7) * kBy + fi * 2 * kBy * kBy
+        const int fl_side = (lane >> 2) & 1, fl_pair = lane & 3;              // flush lanes 0..7: side, pair of rows
+        const int fl_lag = ((fl_side == 0) == !revx) ? 13 : 14;               // memory column 0 is sweep column 0 unless revx
+        const size_t fl_off = (col * nz + zb) * kRec + kBx * kBy + fl_side * kBy + 2 * fl_pair;
+        if (blocked && ey < kBy) {  // rows outside the grid are never written: keep their face entries at u_nan
+            for (int e = lane; e < Cfg<kNF>::kFaceCells; e += 32) FB[e] = DBL_MAX;
+            __syncwarp();
         }
         // per-field bases of the three transfers of this lane: interior pair (loaded and written back), halo source
         double *pu_t[kNF];
         const double *pu_h[kNF];
-        double *pf_st[kNF];  // own face entry (lanes holding memory column 0 or 7 of row jt), written with the pair
-        const bool face_lane = use_faces && (tp == 0 || tp == 3) && act_t && !(kDbg & 16);
+        double *pu_fl[kNF];  // blocked, lanes 0..7: this lane's 16 bytes of the record's face copies
 #pragma unroll
         for (int fi = 0; fi < kNF; ++fi) {
             pu_t[fi] = ufs[fi] + rowt;
-            double *ffaces = use_faces ? a.faces + (size_t)fld[fi] * 2 * per_side : nullptr;
-            pu_h[fi] = (hmode == 3 ? ffaces : ufs[fi]) + offh;
-            pf_st[fi] = face_lane ? ffaces + (tp == 0 ? 0 : 1) * per_side + ((size_t)I * nz + zb) * a.face_ny + (yb + sy * jt) : nullptr;
+            pu_h[fi] = ufs[fi] + offh;
+            pu_fl[fi] = ufs[fi] + fl_off;
         }
 
         int ld_slot = 0, ld_m = 0;
         // steady steps form every global address as (per-task byte base) + zo, one running plane offset in bytes
         const long long zsb = zstride * (long long)sizeof(double);
         long long zo = -(long long)kofs_t * zsb;                            // (ld_m - kofs_t) planes
-        // halo transfer of the same issue; face copies (hmode 3) advance by the face plane stride (running offset zoh)
-        const long long fzsb = fzstride * (long long)sizeof(double);
-        long long zoh = -(long long)kofs_t * fzsb;
+        // the slowness has its own plane stride when blocked (running offset zos)
+        const long long szsb = szstride * (long long)sizeof(double);
+        long long zos = -(long long)kofs_t * szsb;
         const char *bf_t = reinterpret_cast<const char *>(pf_t);
         const char *bu_t[kNF], *bu_h[kNF];
-        char *bu_st[kNF], *bf_st[kNF];
+        char *bu_st[kNF], *bu_fl[kNF];
 #pragma unroll
         for (int fi = 0; fi < kNF; ++fi) {
             bu_t[fi] = reinterpret_cast<const char *>(pu_t[fi]);
-            bu_h[fi] = reinterpret_cast<const char *>(pu_h[fi]) + (long long)(kofs_t - kofs_h) * (hmode == 3 ? fzsb : zsb);
+            bu_h[fi] = reinterpret_cast<const char *>(pu_h[fi]) + (long long)(kofs_t - kofs_h) * zsb;  // halo transfer of the same issue
             bu_st[fi] = reinterpret_cast<char *>(pu_t[fi]) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
-            bf_st[fi] = reinterpret_cast<char *>(pf_st[fi]) - (8 + kPrefetch) * fzsb;
+            // face plane stored in step l: plane l - fl_lag; zo stands at (l + 7 - kofs_t) planes when the stores are issued
+            bu_fl[fi] = reinterpret_cast<char *>(pu_fl[fi]) + (long long)(kofs_t - 7 - fl_lag) * zsb;
         }
-        const long long pf_ahead = (long long)a.l2_prefetch * zsb;
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
@@ -401,38 +432,31 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             } else if (kSteady) {
 #pragma unroll
                 for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, bu_t[fi] + zo);
-                cp_async16(sp + cf_t, bf_t + zo);
-                if (pf_ahead != 0 && k + a.l2_prefetch < ez) {  // planes further ahead: into the L2 only (no shared memory held)
-#pragma unroll
-                    for (int fi = 0; fi < kNF; ++fi) prefetch_l2(bu_t[fi] + zo + pf_ahead);
-                    prefetch_l2(bf_t + zo + pf_ahead);
-                }
+                cp_async16(sp + cf_t, bf_t + zos);
             } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
-                const long long z = (long long)min(max(k, klo), khi) * zstride;
+                const int kc = min(max(k, klo), khi);
 #pragma unroll
-                for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, pu_t[fi] + z);
-                if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + z);
+                for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, pu_t[fi] + (long long)kc * zstride);
+                if (k >= 0 && k < ez) cp_async16(sp + cf_t, pf_t + (long long)kc * szstride);
             }
             const int kh = ld_m - kofs_h;
 #pragma unroll
             for (int fi = 0; fi < kNF; ++fi) {
                 double *sh = sp + fi * kUCells + cu_h;
                 if (kDbg & 4) {
-                } else if (kSteady) {  // full brick: every halo lane copies a pair of u (a face entry with face copies)
-                    if (hmode == 3) cp_async8(sh, bu_h[fi] + zoh);
+                } else if (kSteady) {  // full brick: every halo lane copies a pair (blocked: the x lanes one face entry)
+                    if (hmode == 2) cp_async8(sh, bu_h[fi] + zo);
                     else if (hmode != 0) cp_async16(sh, bu_h[fi] + zo);
                 } else if (hmode == 1) {
                     if (kh >= 0 && kh < ez) cp_async16(sh, pu_h[fi] + (long long)kh * zstride);
                 } else if (hmode == 2) {
                     if (kh >= 0 && kh < ez) cp_async8(sh, pu_h[fi] + (long long)kh * zstride);
-                } else if (hmode == 3) {
-                    if (kh >= 0 && kh < ez) cp_async8(sh, pu_h[fi] + (long long)kh * fzstride);
                 }
             }
             cp_async_commit();
             ++ld_m;
             zo += zsb;
-            zoh += fzsb;
+            zos += szsb;
             ld_slot = (ld_slot + kSlot == kRing * kSlot) ? 0 : ld_slot + kSlot;
         };
         for (int m = 0; m < 4 + kPrefetch; ++m) issue_slot(std::false_type());
@@ -440,7 +464,7 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         // ---- compute descriptors
         const int qx = revx ? kBx - 1 - li : li;            // memory column of this lane's sweep column
         const int cu0 = (j0 + 1) * kURow + qx + 2;          // ring cell of compute column c: cu0 + c * kURow (+ fi * kUCells)
-        const int cf0 = kNF * kUCells + j0 * kBx + qx;
+        const int cf0 = kNF * kUCells + j0 * kFRow + qx;
         bool act[kNC];
 #pragma unroll
         for (int c = 0; c < kNC; ++c) act[c] = j0 + c < ey;
@@ -508,7 +532,7 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
                     const double yp = c + 1 < kNC ? zp[q + 1] : pp[(c + 1) * kURow];
                     uy[q] = dmin2(ym, yp);
                     uz[q] = dmin2(zm[q], zp[q]);
-                    fh[q] = U[oc + cf0 + c * kBx];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
+                    fh[q] = U[oc + cf0 + c * kFRow];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
                 }
             }
             if (kDbg & 1) {
@@ -540,10 +564,19 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
                         const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + fi * kUCells + cu_t);
                         if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st[fi] + zo), v);
                         else __stcg(reinterpret_cast<double2 *>(pu_t[fi] + (long long)ks * zstride), v);
-                        if (face_lane) {
-                            const double fv = tp == 0 ? v.x : v.y;
-                            if (kSteady) __stcg(reinterpret_cast<double *>(bf_st[fi] + zoh), fv);
-                            else __stcg(pf_st[fi] + (long long)ks * fzstride, fv);
+                        if (face_lane) FB[fi * 2 * kBy * kBy + fb_t + (ks & 7) * kBy] = tp == 0 ? v.x : v.y;
+                    }
+                }
+                if (blocked) {  // lanes 0..7: the face plane whose last row arrived in this step
+                    __syncwarp();
+                    const int kf = l - fl_lag;
+                    if (lane < 8 && !(kDbg & 8) && (kSteady || (unsigned)kf < (unsigned)ez)) {
+#pragma unroll
+                        for (int fi = 0; fi < kNF; ++fi) {
+                            if (fi > 0 && !st_second) continue;
+                            const double2 v = *reinterpret_cast<const double2 *>(FB + fi * 2 * kBy * kBy + fl_side * (kBy * kBy) + (kf & 7) * kBy + 2 * fl_pair);
+                            if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_fl[fi] + zo), v);
+                            else __stcg(reinterpret_cast<double2 *>(pu_fl[fi] + (long long)kf * zstride), v);
                         }
                     }
                 }
@@ -568,7 +601,7 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         // steady window: all transfers, updates and stores of the step touch in-brick nodes of a full
         // brick that is not on the grid's x faces and holds no boundary-condition node; it runs in whole
         // publication chunks with no per-step bookkeeping
-        const bool full = ey == kBy && !hasbc && ((use_faces && !(kDbg & 32)) || (x_lo >= 2 && x_lo + kBx + 1 <= nx - 1));
+        const bool full = ey == kBy && !hasbc;
         int s_lo = (kBy + 6 + publish - 1) & ~(publish - 1), s_hi = (ez - 3 - kPrefetch) & ~(publish - 1);
         if (!full || s_hi <= s_lo) s_lo = s_hi = nsteps;
         int l = 0;

@@ -224,12 +224,13 @@ def test_homogeneous_tables(gpu_ctx):
     assert np.array_equal(t, ref)
 
 
-@pytest.mark.parametrize("faces", [0, 1])
-def test_two_fields_per_task(gpu_ctx, faces):
+@pytest.mark.parametrize("natural", [0, 1])
+def test_two_fields_per_task(gpu_ctx, natural):
     """The pair flavour of sweep_bricks16_kernel (two fields of one slowness model walk a brick together, forced here
     from 2 active fields on): 9 fields over 2 models -- an odd count per model, so one task carries a single field
     whose second copy is computed and never stored --, several sources in one field, a grid with partial bricks in y
-    and more than one brick along z; with and without the compact x-face copies.  Bit-equal to the oracle."""
+    and more than one brick along z; on the kernel's blocked layout (default) and on the caller's [z][y][x] layout.
+    Bit-equal to the oracle."""
     from mceik_b200.eikonal import EikonalSolver
     nx, ny, nz, h = 40, 28, 300, 200.0
     n = nx * ny * nz
@@ -239,12 +240,12 @@ def test_two_fields_per_task(gpu_ctx, faces):
     xs, ys, zs = cases.interior_sources(nf + 1, nx, ny, nz, h, seed=12)
     src_ptr = np.array([0, 2] + list(range(3, nf + 2)), np.int32)  # field 0 has two sources
     ts = np.linspace(0.0, 0.5, nf + 1)
-    gpu_ctx.set_tuning("PAIR_MIN", 2).set_tuning("FACES", faces)
+    gpu_ctx.set_tuning("PAIR_MIN", 2).set_tuning("NATURAL", natural)
     try:
         sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
         u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, src_ptr=src_ptr)
     finally:
-        gpu_ctx.set_tuning("PAIR_MIN", 24).set_tuning("FACES", 0)
+        gpu_ctx.set_tuning("PAIR_MIN", 24).set_tuning("NATURAL", 0)
     assert not ferr.any()
     for f in range(nf):
         a, b = src_ptr[f], src_ptr[f + 1]
