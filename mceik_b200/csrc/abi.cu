@@ -64,7 +64,6 @@ struct mceik_ctx {
         int publish = -1;     // steps between progress publications (power of two)
         int publisher = -1;   // 0 / 1: force one publication flavour
         int no_stagger = 0;   // 1: one field group in the ticket order
-        int pair_min = 24;    // two fields per task from this many active fields on (0 = never)
         int natural = 0;      // 1: bricks16 works on the caller's [z][y][x] layout instead of the blocked one
         int batch = 0;        // sequential field batches (experiment)
         int trace = 0, stats = 0, debug = 0;
@@ -86,7 +85,7 @@ namespace {
 int *tuning_slot(mceik_ctx *c, const char *key) {
     struct { const char *name; int *p; } const tab[] = {
         {"ZC", &c->tune.zc}, {"BY", &c->tune.by}, {"NO16", &c->tune.no16}, {"PUBLISH", &c->tune.publish},
-        {"PUBLISHER", &c->tune.publisher}, {"NO_STAGGER", &c->tune.no_stagger}, {"PAIR_MIN", &c->tune.pair_min},
+        {"PUBLISHER", &c->tune.publisher}, {"NO_STAGGER", &c->tune.no_stagger}, 
         {"NATURAL", &c->tune.natural}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
         {"STATS", &c->tune.stats}, {"DEBUG", &c->tune.debug}, {"LOCATE_NO_ALIGN", &c->tune.locate_no_align}};
     for (const auto &e : tab)
@@ -94,7 +93,7 @@ int *tuning_slot(mceik_ctx *c, const char *key) {
     return nullptr;
 }
 void tuning_from_env(mceik_ctx *c) {
-    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "PAIR_MIN", "NATURAL", "BATCH", "TRACE",
+    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "NATURAL", "BATCH", "TRACE",
                           "STATS", "DEBUG"}) {
         const std::string name = std::string("MCEIK_FSM_") + k;
         if (const char *e = getenv(name.c_str())) *tuning_slot(c, k) = atoi(e);
@@ -178,7 +177,6 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         MCEIK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming));
     }
 
-    if (!d_u) d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * nfields));
     ctx->plan.build(nx, ny, nz, st);
     const fsm::TilePlan &pl = ctx->plan;
     const bool bricks = ctx->fsm_algo == MCEIK_FSM_ALGO_BRICKS;
@@ -235,9 +233,6 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     const int *d_recf = upload(ctx->ws_meta, o_recf, rec_field, st);
     const int *d_recn = upload(ctx->ws_meta, o_recn, rec_node, st);
 
-    // ---- u = HUGE everywhere, then the stencil values (fsm3d.f90:782-834)
-    fsm::launch_fill(d_u, N * nfields, DBL_MAX, st);
-    fsm::launch_apply_bcs(nfields, N, d_fmodel, d_recptr, d_recs, d_slow, d_u, st);
 
     // ---- iterations (fsm3d.f90:62-96).  One launch = 8 sweeps of every still-active field.
     std::vector<int> active, it(nfields, 0);
@@ -269,15 +264,21 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     const bool blocked = bricks16 && !ctx->tune.natural;
     const size_t Nb = blocked ? fsm::blocked_field_doubles(nx, ny, nz) : N;  // doubles per field the iterations work on
     const double *d_fh = nullptr;
-    double *d_w = d_u, *d_w0 = nullptr;  // fields / start-of-iteration copy the sweeps and the convergence test use
-    if (blocked) {
+    double *d_w = nullptr, *d_w0 = nullptr;  // fields / start-of-iteration copy the sweeps and the convergence test use
+    // ---- u = HUGE everywhere, then the stencil values (fsm3d.f90:782-834)
+    if (blocked) {  // the caller's d_u (may be NULL: tables only) is written once, when a field has converged
         double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * fsm::blocked_slowness_doubles(nx, ny, nz) * nmodels));
         fsm::launch_scale_slowness_blocked(nx, ny, nz, nmodels, g->h, d_slow, fh, st);
         d_fh = fh;
         d_w = static_cast<double *>(ctx->ws_ub.ensure(sizeof(double) * Nb * nfields));
         d_w0 = static_cast<double *>(ctx->ws_u0b.ensure(sizeof(double) * Nb * nfields));
-        fsm::launch_block_fields(nx, ny, nz, nfields, d_u, d_w, st);
+        fsm::launch_fill(d_w, Nb * nfields, DBL_MAX, st);
+        fsm::launch_apply_bcs_blocked(nfields, nx, ny, nz, d_fmodel, d_recptr, d_recs, d_slow, d_w, st);
     } else {
+        if (!d_u) d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * nfields));
+        d_w = d_u;
+        fsm::launch_fill(d_u, N * nfields, DBL_MAX, st);
+        fsm::launch_apply_bcs(nfields, N, d_fmodel, d_recptr, d_recs, d_slow, d_u, st);
         if (bricks16) {
             double *fh = static_cast<double *>(ctx->ws_fh.ensure(sizeof(double) * N * nmodels));
             fsm::launch_scale_slowness(N * nmodels, g->h, d_slow, fh, st);
@@ -304,31 +305,17 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
                                          d_u, st);
             fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_u, d_u0, d_nonconv, st);
         } else if (bricks) {
-            // many active fields: two fields of one slowness model per task (BrickArgs::fields_per_task)
-            const bool pairs = bricks16 && ctx->tune.pair_min > 0 && (int)active.size() >= ctx->tune.pair_min;
-            std::vector<int> units;
-            if (pairs) {
-                std::map<int, std::vector<int>> by_model;
-                for (int f : active) by_model[fmodel[f]].push_back(f);
-                for (auto &kv : by_model)
-                    for (size_t i = 0; i < kv.second.size(); i += 2)
-                        units.push_back(kv.second[i] | (kv.second[i + 1 < kv.second.size() ? i + 1 : i] << 16));
-            } else {
-                units = active;
-            }
-            const int *d_active = upload(ctx->ws_meta, o_active, active, st);  // convergence test: plain field ids
-            const int *d_units = upload(ctx->ws_meta, o_units, units, st);
+            const int *d_active = upload(ctx->ws_meta, o_active, active, st);
             fsm::BrickArgs a;
             a.nx = nx; a.ny = ny; a.nz = nz;
             a.nbx = bp.nbx; a.nby = bp.nby; a.nbz = bp.nbz; a.nbricks = bp.nbricks; a.nblevels = bp.nblevels; a.zc = bp.zc; a.by = bp.by;
-            a.nfields_active = (int)units.size();
-            a.fields_per_task = pairs ? 2 : 1;
+            a.nfields_active = (int)active.size();
             // few fields: short publication interval (tight pipelining of the brick wavefront);
             // many fields: parallelism is plentiful, publish less often (each publication costs a fence)
             a.publish = active.size() >= 48 ? 16 : (active.size() > 16 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
             if (ctx->tune.publish > 0) a.publish = ctx->tune.publish;
             a.h = g->h;
-            a.active = d_units; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
+            a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
             a.u = d_w; a.blocked = blocked ? 1 : 0;
             a.brick_order = ctx->bplan.brick_order.as<int>();
             a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
@@ -338,8 +325,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.vptr = nullptr; a.nf0 = a.nfields_active; a.stagger = 0; a.batch = 0;
             // few active fields: a publisher warp per CTA takes the release fences off the sweeping warps (+8-12 % up to
             // 11 fields, +1 % at 16, nothing beyond; profiles/kernel_evolution_r1.md)
-            a.publisher = active.size() <= 16 && !pairs ? 1 : 0;
-            if (ctx->tune.publisher >= 0 && !pairs) a.publisher = ctx->tune.publisher != 0;
+            a.publisher = active.size() <= 16 ? 1 : 0;
+            if (ctx->tune.publisher >= 0) a.publisher = ctx->tune.publisher != 0;
             if (bricks16) {  // two field groups half a sweep apart (see BrickArgs)
                 const int nl = bp.nblevels, nfa = a.nfields_active;
                 a.nf0 = (nfa + 1) / 2;
@@ -360,7 +347,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             else fsm::launch_iteration_bricks(a, st);
             MCEIK_CUDA(cudaEventRecord(ctx->ev1, st));
             ctx->last_sweep_launches += 1;
-            fsm::launch_convergence(Nb, (int)active.size(), d_active, g->tol, d_w, d_w0, d_nonconv, st);
+            if (blocked) fsm::launch_convergence_blocked(nx, ny, nz, (int)active.size(), d_active, g->tol, d_w, d_w0, d_nonconv, st);
+            else fsm::launch_convergence(N, (int)active.size(), d_active, g->tol, d_w, d_w0, d_nonconv, st);
         } else {
             // group the active fields by slowness model, up to kMaxSlots per CTA
             std::map<int, std::vector<int>> by_model;
@@ -426,11 +414,11 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
                 finished.push_back(f);
             }
         }
-        if (blocked && !finished.empty()) {  // back into the caller's layout
+        if (blocked && !finished.empty()) {  // into the caller's layout: fp64 field and / or fp32 table, one pass
             const int *d_fin = upload(ctx->ws_meta, o_units, finished, st);
-            fsm::launch_unblock_fields(nx, ny, nz, (int)finished.size(), d_fin, d_w, d_u, st);
+            fsm::launch_unblock_fields(nx, ny, nz, (int)finished.size(), d_fin, d_w, d_u, d_tables, ldtab, st);
         }
-        if (ctx->early_u && !finished.empty()) {  // copy them back while the others keep iterating
+        if (ctx->early_u && d_u && !finished.empty()) {  // copy them back while the others keep iterating
             if (blocked) {
                 MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, st));
                 MCEIK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fin, 0));
@@ -443,6 +431,8 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         }
         active.swap(still);
     }
+    if (blocked && g->maxit < 1)  // no iteration ran: the fields are their boundary conditions
+        fsm::launch_unblock_fields(nx, ny, nz, nfields, nullptr, d_w, d_u, d_tables, ldtab, st);
     int rc = 0;
     for (int f = 0; f < nfields; ++f) {
         ctx->last_updates += (long long)N * 8 * it[f];
@@ -450,7 +440,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
         if (field_ierr) field_ierr[f] = ferr[f];
         if (ferr[f]) rc = 1;
     }
-    if (d_tables) fsm::launch_pack_tables(nfields, N, ldtab, d_u, d_tables, st);
+    if (d_tables && !blocked) fsm::launch_pack_tables(nfields, N, ldtab, d_u, d_tables, st);
     return rc;
 }
 
@@ -660,7 +650,7 @@ int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int
         const size_t N = (size_t)grid->nx * grid->ny * grid->nz;
         double *d_slow = static_cast<double *>(ctx->ws_slow.ensure(sizeof(double) * N * nmodels));
         MCEIK_CUDA(cudaMemcpyAsync(d_slow, slow, sizeof(double) * N * nmodels, cudaMemcpyHostToDevice, ctx->stream));
-        double *d_u = static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * std::max(nfields, 1)));
+        double *d_u = u ? static_cast<double *>(ctx->ws_u.ensure(sizeof(double) * N * std::max(nfields, 1))) : nullptr;
         float *d_tab = nullptr;
         if (tables) d_tab = static_cast<float *>(ctx->ws_tab.ensure(sizeof(float) * ldtab * std::max(nfields, 1)));
         // pinned destination: copy every field back as soon as it has converged, overlapped with the sweeps of

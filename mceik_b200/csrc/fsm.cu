@@ -501,6 +501,79 @@ __global__ void block_fields_kernel(int nx, int ny, int nz, const double *__rest
     }
 }
 
+// EIKONAL3D_SETBCS on the blocked layout: one thread per field applies its records in source order (fsm3d.f90:810-833)
+// to the node's record entry and, for nodes of columns 0 / 7 of a brick, to the face copy
+__global__ void apply_bcs_blocked_kernel(int nfields, int nx, int ny, int nz, const int *__restrict__ field_model,
+                                         const int *__restrict__ rec_ptr, const BcRecord *__restrict__ recs,
+                                         const double *__restrict__ slow, double *__restrict__ ub) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfields) return;
+    const int nbx = nx / 8, nby = (ny + 7) / 8;
+    const size_t nxy = (size_t)nx * ny, n = nxy * nz;
+    const double *sl = slow + (size_t)field_model[f] * n;
+    double *uf = ub + (size_t)f * ((size_t)nbx * nby * nz * kRecU);
+    for (int r = rec_ptr[f]; r < rec_ptr[f + 1]; ++r) {
+        const BcRecord rec = recs[r];
+        const int x = (int)(rec.node % nx), y = (int)((rec.node / nx) % ny), z = (int)(rec.node / nxy);
+        double *p = uf + (((size_t)(y >> 3) * nbx + (x >> 3)) * nz + z) * kRecU;
+        const int e = (y & 7) * 8 + (x & 7);
+        const double t = __dadd_rn(rec.ts, __dmul_rn(rec.d, sl[rec.node]));  // ts + d*slow (:826,828)
+        const double v = rec.collocated ? t : fmin(p[e], t);
+        p[e] = v;
+        if ((x & 7) == 0) p[64 + (y & 7)] = v;
+        if ((x & 7) == 7) p[72 + (y & 7)] = v;
+    }
+}
+
+void launch_apply_bcs_blocked(int nfields, int nx, int ny, int nz, const int *d_field_model, const int *d_rec_ptr,
+                              const BcRecord *d_recs, const double *d_slow, double *d_ub, cudaStream_t st) {
+    if (nfields == 0) return;
+    apply_bcs_blocked_kernel<<<(nfields + 63) / 64, 64, 0, st>>>(nfields, nx, ny, nz, d_field_model, d_rec_ptr, d_recs, d_slow, d_ub);
+    MCEIK_LAUNCH_CHECK();
+}
+
+// convergence test on the blocked layout: the 64 nodes of every record (the face copies are duplicates; rows
+// beyond ny hold u_nan in both arrays and compare equal), u0 = u for those entries (fsm3d.f90:86-90)
+__global__ void convergence_blocked_kernel(size_t nrec, const int *__restrict__ active_fields, double tol,
+                                           const double *__restrict__ u, double *__restrict__ u0,
+                                           unsigned long long *__restrict__ nonconv) {
+    const int f = active_fields[blockIdx.y];
+    const double *uf = u + (size_t)f * nrec * kRecU;
+    double *u0f = u0 + (size_t)f * nrec * kRecU;
+    const size_t n2 = nrec * 32;  // pairs of nodes
+    unsigned int bad = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n2; i0 += 4 * stride) {
+        double2 v[4], o[4];  // four independent streams per thread keep enough bytes in flight
+        size_t off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const size_t i = i0 + q * stride;
+            off[q] = (i >> 5) * kRecU + (i & 31) * 2;
+            if (i < n2) { v[q] = __ldcs(reinterpret_cast<const double2 *>(uf + off[q])); o[q] = __ldcs(reinterpret_cast<const double2 *>(u0f + off[q])); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q * stride < n2) {
+                if (!(fabs(__dsub_rn(o[q].x, v[q].x)) < tol)) ++bad;
+                if (!(fabs(__dsub_rn(o[q].y, v[q].y)) < tol)) ++bad;
+                __stcs(reinterpret_cast<double2 *>(u0f + off[q]), v[q]);
+            }
+        }
+    }
+    for (int off2 = 16; off2 > 0; off2 >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, off2);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonconv + f, (unsigned long long)bad);
+}
+
+void launch_convergence_blocked(int nx, int ny, int nz, int nfields, const int *d_active_fields, double tol, const double *d_ub,
+                                double *d_u0b, unsigned long long *d_nonconv, cudaStream_t st) {
+    if (nfields == 0) return;
+    const size_t nrec = (size_t)(nx / 8) * ((ny + 7) / 8) * nz;
+    dim3 grid((unsigned)std::min<size_t>((nrec * 32 + 1023) / 1024, 148 * 4), nfields);
+    convergence_blocked_kernel<<<grid, 256, 0, st>>>(nrec, d_active_fields, tol, d_ub, d_u0b, d_nonconv);
+    MCEIK_LAUNCH_CHECK();
+}
+
 void launch_block_fields(int nx, int ny, int nz, int nfields, const double *d_u, double *d_ub, cudaStream_t st) {
     if (nfields == 0) return;
     const size_t total = blocked_field_doubles(nx, ny, nz);
@@ -509,25 +582,28 @@ void launch_block_fields(int nx, int ny, int nz, int nfields, const double *d_u,
     MCEIK_LAUNCH_CHECK();
 }
 
+// blocked records -> the caller's layout: fp64 field (u != nullptr) and / or fp32 table (tab != nullptr; SNGL(u),
+// fsm3d.f90:1870-1872) of the listed fields.  One thread per node: the writes are coalesced.
 __global__ void unblock_fields_kernel(int nx, int ny, int nz, const int *__restrict__ fields, const double *__restrict__ ub,
-                                      double *__restrict__ u) {
+                                      double *__restrict__ u, float *__restrict__ tab, size_t ldtab) {
     const int f = fields ? fields[blockIdx.y] : blockIdx.y;
     const int nbx = nx / 8, nby = (ny + 7) / 8;
     const size_t nxy = (size_t)nx * ny, N = nxy * nz, stride = (size_t)gridDim.x * blockDim.x;
     const double *ubf = ub + (size_t)f * ((size_t)nbx * nby * nz * kRecU);
-    double *uf = u + (size_t)f * N;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += stride) {  // t = node: coalesced writes
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += stride) {
         const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / nxy);
-        uf[t] = ubf[(((size_t)(y >> 3) * nbx + (x >> 3)) * nz + z) * kRecU + (y & 7) * 8 + (x & 7)];
+        const double v = __ldcs(ubf + (((size_t)(y >> 3) * nbx + (x >> 3)) * nz + z) * kRecU + (y & 7) * 8 + (x & 7));
+        if (u) u[(size_t)f * N + t] = v;
+        if (tab) tab[(size_t)f * ldtab + t] = __double2float_rn(v);
     }
 }
 
 void launch_unblock_fields(int nx, int ny, int nz, int nfields, const int *d_fields, const double *d_ub, double *d_u,
-                           cudaStream_t st) {
-    if (nfields == 0) return;
+                           float *d_tables, size_t ldtab, cudaStream_t st) {
+    if (nfields == 0 || (!d_u && !d_tables)) return;
     const size_t N = (size_t)nx * ny * nz;
     dim3 grid((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), nfields);
-    unblock_fields_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, d_fields, d_ub, d_u);
+    unblock_fields_kernel<<<grid, 256, 0, st>>>(nx, ny, nz, d_fields, d_ub, d_u, d_tables, ldtab);
     MCEIK_LAUNCH_CHECK();
 }
 

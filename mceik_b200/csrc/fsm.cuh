@@ -75,9 +75,7 @@ struct BrickPlan {
 struct BrickArgs {
     int nx, ny, nz;
     int nbx, nby, nbz, nbricks, nblevels, zc, by;
-    int nfields_active;       // bricks16: number of tasks' worth of fields = entries of `active` (pairs count once)
-    int fields_per_task;      // bricks16: 1, or 2 = active[] holds f0 | f1 << 16, two fields of one slowness model
-                              // walked together (f1 == f0: a single field); other kernels: 1
+    int nfields_active;
     int publish;              // a sweeping warp publishes its progress every `publish` steps (4, 8 or 16; a power of two)
     double h;
     const int *active;        // [nfields_active] field ids
@@ -162,12 +160,16 @@ void launch_convergence(size_t n, int nfields, const int *d_active_fields, doubl
 void launch_mark_bcs(int nrec, const int *d_rec_field, const int *d_rec_node, size_t n, uint8_t *d_lupd,
                      cudaStream_t st);
 // Blocked layout of the bricks16 kernel (BrickArgs::blocked).  block: d_ub[f] = records of d_u[f] for every field
-// (u_nan in rows beyond ny); unblock: d_u[f] = nodes of d_ub[f] for the listed fields (d_fields == nullptr: all).
+// (u_nan in rows beyond ny); unblock: nodes of d_ub[f] for the listed fields (d_fields == nullptr: all).
 size_t blocked_field_doubles(int nx, int ny, int nz);
 size_t blocked_slowness_doubles(int nx, int ny, int nz);
 void launch_block_fields(int nx, int ny, int nz, int nfields, const double *d_u, double *d_ub, cudaStream_t st);
 void launch_unblock_fields(int nx, int ny, int nz, int nfields, const int *d_fields, const double *d_ub, double *d_u,
-                           cudaStream_t st);
+                           float *d_tables, size_t ldtab, cudaStream_t st);  // fp64 field and / or fp32 table (either may be null)
+void launch_apply_bcs_blocked(int nfields, int nx, int ny, int nz, const int *d_field_model, const int *d_rec_ptr,
+                              const BcRecord *d_recs, const double *d_slow, double *d_ub, cudaStream_t st);
+void launch_convergence_blocked(int nx, int ny, int nz, int nfields, const int *d_active_fields, double tol, const double *d_ub,
+                                double *d_u0b, unsigned long long *d_nonconv, cudaStream_t st);
 // d_out[model][brick column][z][64] = d_slow[model][z][y][x] * h (1.0 in rows beyond ny)
 void launch_scale_slowness_blocked(int nx, int ny, int nz, int nmodels, double h, const double *d_slow, double *d_out,
                                    cudaStream_t st);

@@ -55,19 +55,21 @@ constexpr int kMaxZc = 256;
 constexpr int kProgShift = 12;
 constexpr int kLead = kBy + 3;
 constexpr int kRec = kBx * kBy + 2 * kBy;          // blocked layout: doubles per brick plane (64 nodes + the two x-face copies)
+constexpr int kFacePlanes = 16;                    // planes of the face staging ring (a plane is written over 9 steps, stored the step after)
 constexpr int kBcMax = 16;                         // planes of one brick that hold boundary-condition nodes of one field
-// kNF fields of one slowness model walk the same brick in one task (template parameter of the kernel): their ring
-// slots sit side by side ([field 0 rows][field 1 rows][slowness]), the slowness tile is loaded once, every address
-// and every wait / publication is shared, and a lane advances 2 * kNF independent update chains.
-template <int kNF>
-struct Cfg {
-    static constexpr int kWarps = kNF == 2 ? 8 : 12;
-    static constexpr int kSlot = kNF * kUCells + kFCells;  // 182 / 284 doubles, 16-byte aligned
-    static constexpr int kBcBytes = kNF * kBcMax * 16;       // [kNF][kBcMax] masks (8 B), then [kNF][kBcMax] planes (4 B, padded)
-    static constexpr int kFaceCells = kNF * 2 * kBy * kBy;   // blocked layout: [field][x side][plane & 7][row] face values on
-                                                             // their way to the brick records (see BrickArgs::blocked)
-    static constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot + kFaceCells) + kBcBytes;
-};
+// Fields walked per task.  A flavour with two fields of one slowness model per task (slots side by side, slowness tile
+// loaded once, 4 update chains per lane, 8 warps per SM) was built and measured slower at every field count
+// (profiles/kernel_evolution_r2.md); the per-field loops below are what is left of it.
+constexpr int kNF = 1;
+#ifndef MCEIK_B16_WARPS
+#define MCEIK_B16_WARPS 12
+#endif
+constexpr int kWarps = MCEIK_B16_WARPS;
+constexpr int kSlot = kNF * kUCells + kFCells;      // 182 doubles, 16-byte aligned
+constexpr int kBcBytes = kNF * kBcMax * 16;         // [kNF][kBcMax] masks (8 B), then [kNF][kBcMax] planes (4 B, padded)
+constexpr int kFaceCells = kNF * 2 * kFacePlanes * kBy;  // blocked layout: [field][x side][plane & 15][row] face values on
+                                                         // their way to the brick records (see BrickArgs::blocked)
+constexpr size_t kWarpSmem = sizeof(double) * (size_t)(kRing * kSlot + kFaceCells) + kBcBytes;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -76,6 +78,15 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+// predicated forms: no branch around the copy (the halo lanes of a steady step differ only in a predicate)
+__device__ __forceinline__ void cp_async16_if(bool p, void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(s), "l"(gsrc), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ void cp_async8_if(bool p, void *smem_dst, const void *gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 8; }" ::"r"(s), "l"(gsrc), "r"((int)p) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -115,10 +126,9 @@ __device__ __forceinline__ void st_relaxed_gpu(int *p, int v) {
 
 }  // namespace
 
-template <bool kPub, int kNF>
-__global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
-    constexpr int kWarps = Cfg<kNF>::kWarps, kSlot = Cfg<kNF>::kSlot, kNQ = kNF * kNC;
-    constexpr size_t kWarpSmem = Cfg<kNF>::kWarpSmem;
+template <bool kPub>
+__global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const BrickArgs a) {
+    constexpr int kNQ = kNF * kNC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ Mail mail[kWarps];
@@ -170,8 +180,8 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
         }
     };
     double *U = reinterpret_cast<double *>(smem_raw + (size_t)warp * kWarpSmem);  // [kRing][kSlot]
-    double *FB = U + kRing * kSlot;                                                            // [kNF][2][8][8]
-    unsigned long long *bc_mask = reinterpret_cast<unsigned long long *>(FB + Cfg<kNF>::kFaceCells);  // [kNF][kBcMax]
+    double *FB = U + kRing * kSlot;                                                            // [kNF][2][kFacePlanes][8]
+    unsigned long long *bc_mask = reinterpret_cast<unsigned long long *>(FB + kFaceCells);  // [kNF][kBcMax]
     int *bc_plane = reinterpret_cast<int *>(bc_mask + kNF * kBcMax);                           // [kNF][kBcMax], -1 = free
 
     const int nx = a.nx, ny = a.ny, nz = a.nz;
@@ -209,14 +219,9 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             task = decode_ticket(t, a.vptr, a.blevel_ptr, nl, a.stagger, nf0, nf1);
         }
         const int s = task.sweep;
-        // the task's fields: active[] holds f0 | f1 << 16 when kNF == 2 (f1 == f0: a single field, whose second copy
-        // is computed from the same inputs and never stored)
-        const int unit = __ldg(a.active + task.fidx);
         int fld[kNF];
-        fld[0] = unit & 0xffff;
-        if (kNF == 2) fld[kNF - 1] = (unit >> 16) & 0xffff;
+        fld[0] = __ldg(a.active + task.fidx);
         const int f = fld[0];
-        const bool st_second = kNF == 2 && fld[kNF - 1] != fld[0];
         const int packed = __ldg(a.brick_order + __ldg(a.blevel_ptr + task.level) + task.bidx);
         const bool revx = (s & 1) != 0, revy = (s & 2) != 0, revz = (s & 4) != 0;  // fsm3d.f90:46-53
         int I = packed & 1023, J = (packed >> 10) & 1023, K = packed >> 20;
@@ -257,8 +262,8 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
                 // Blocked layout: the x-halo comes from the neighbour's face copies, written one whole plane at a
-                // time 14 steps after the plane was entered: x needs 1 step MORE lead than y.
-                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? -1 : kBy - 2) : 0);
+                // time 15 steps after the plane was entered: x needs 2 steps MORE lead than y.
+                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? -2 : kBy - 2) : 0);
                 seen = max(seen, ahead);
                 if (seen < need)
                     while ((seen = ld_acquire_gpu(up_ptr)) < need) __nanosleep(200);
@@ -383,16 +388,17 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             offh = blocked ? (((size_t)(yh / kBy) * a.nbx + I) * nz + zb) * kRec + (size_t)(yh % kBy) * kBx + 2 * hp
                            : (size_t)zb * nxy + (size_t)yh * nx + x_lo + 2 * hp;
         }
-        // blocked: values of memory columns 0 and 7 go to the face staging FB[field][side][plane & 7][row] when their
-        // pair is written back, and a whole plane of a side (64 contiguous bytes of the record) is stored once its
-        // 8 rows are in: 13 steps after the plane was entered for the side of sweep column 0, 14 for sweep column 7
+        // blocked: values of memory columns 0 and 7 go to the face staging FB[field][side][plane & 15][row] when their
+        // pair is written back, and a whole plane of a side (64 contiguous bytes of the record) is stored the step
+        // after its 8 rows are in (so the step's own __syncwarp orders it): 14 steps after the plane was entered for
+        // the side of sweep column 0, 15 for sweep column 7
         const bool face_lane = blocked && (tp == 0 || tp == 3) && act_t;
-        const int fb_t = (tp == 0 ? 0 : 1) * (kBy * kBy) + (yt - y_lo);       // + (plane & 7) * kBy + fi * 2 * kBy * kBy
-        const int fl_side = (lane >> 2) & 1, fl_pair = lane & 3;              // flush lanes 0..7: side, pair of rows
-        const int fl_lag = ((fl_side == 0) == !revx) ? 13 : 14;               // memory column 0 is sweep column 0 unless revx
+        const int fb_t = (tp == 0 ? 0 : 1) * (kFacePlanes * kBy) + (yt - y_lo);  // + (plane & 15) * kBy + fi * 2 * kFacePlanes * kBy
+        const int fl_side = (lane >> 2) & 1, fl_pair = lane & 3;                 // flush lanes 0..7: side, pair of rows
+        const int fl_lag = ((fl_side == 0) == !revx) ? 14 : 15;                  // memory column 0 is sweep column 0 unless revx
         const size_t fl_off = (col * nz + zb) * kRec + kBx * kBy + fl_side * kBy + 2 * fl_pair;
         if (blocked && ey < kBy) {  // rows outside the grid are never written: keep their face entries at u_nan
-            for (int e = lane; e < Cfg<kNF>::kFaceCells; e += 32) FB[e] = DBL_MAX;
+            for (int e = lane; e < kFaceCells; e += 32) FB[e] = DBL_MAX;
             __syncwarp();
         }
         // per-field bases of the three transfers of this lane: interior pair (loaded and written back), halo source
@@ -444,9 +450,9 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             for (int fi = 0; fi < kNF; ++fi) {
                 double *sh = sp + fi * kUCells + cu_h;
                 if (kDbg & 4) {
-                } else if (kSteady) {  // full brick: every halo lane copies a pair (blocked: the x lanes one face entry)
-                    if (hmode == 2) cp_async8(sh, bu_h[fi] + zo);
-                    else if (hmode != 0) cp_async16(sh, bu_h[fi] + zo);
+                } else if (kSteady) {  // full brick: every halo lane copies a pair (the x lanes one value)
+                    cp_async8_if(hmode == 2, sh, bu_h[fi] + zo);
+                    cp_async16_if(hmode == 1, sh, bu_h[fi] + zo);
                 } else if (hmode == 1) {
                     if (kh >= 0 && kh < ez) cp_async16(sh, pu_h[fi] + (long long)kh * zstride);
                 } else if (hmode == 2) {
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
             }
         }
 
-        const int nsteps = ez + kBy + 6;
+        const int nsteps = ez + kBy + 6 + (blocked ? 1 : 0);  // blocked: one more step stores the last face plane
         auto step_core = [&](int l, auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             issue_slot(steady_tag);
@@ -560,21 +566,19 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
                 if (!(kDbg & 8) && (kSteady || (act_t && (unsigned)ks < (unsigned)ez))) {
 #pragma unroll
                     for (int fi = 0; fi < kNF; ++fi) {
-                        if (fi > 0 && !st_second) continue;  // the second copy of a single field is never stored
                         const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + fi * kUCells + cu_t);
                         if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st[fi] + zo), v);
                         else __stcg(reinterpret_cast<double2 *>(pu_t[fi] + (long long)ks * zstride), v);
-                        if (face_lane) FB[fi * 2 * kBy * kBy + fb_t + (ks & 7) * kBy] = tp == 0 ? v.x : v.y;
+                        if (face_lane) FB[fi * 2 * kFacePlanes * kBy + fb_t + (ks & (kFacePlanes - 1)) * kBy] = tp == 0 ? v.x : v.y;
                     }
                 }
-                if (blocked) {  // lanes 0..7: the face plane whose last row arrived in this step
-                    __syncwarp();
+                if (blocked) {  // lanes 0..7: the face plane whose last row arrived in the previous step
                     const int kf = l - fl_lag;
                     if (lane < 8 && !(kDbg & 8) && (kSteady || (unsigned)kf < (unsigned)ez)) {
 #pragma unroll
                         for (int fi = 0; fi < kNF; ++fi) {
-                            if (fi > 0 && !st_second) continue;
-                            const double2 v = *reinterpret_cast<const double2 *>(FB + fi * 2 * kBy * kBy + fl_side * (kBy * kBy) + (kf & 7) * kBy + 2 * fl_pair);
+                            const double2 v = *reinterpret_cast<const double2 *>(FB + fi * 2 * kFacePlanes * kBy + fl_side * (kFacePlanes * kBy) +
+                                                                                 (kf & (kFacePlanes - 1)) * kBy + 2 * fl_pair);
                             if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_fl[fi] + zo), v);
                             else __stcg(reinterpret_cast<double2 *>(pu_fl[fi] + (long long)kf * zstride), v);
                         }
@@ -632,14 +636,14 @@ __global__ void __launch_bounds__(Cfg<kNF>::kWarps * 32, 1) sweep_bricks16_kerne
 }
 
 namespace {
-template <bool kPub, int kNF>
+template <bool kPub>
 void launch_flavour(const BrickArgs &a, int nsm, cudaStream_t st) {
-    constexpr int kWarps = Cfg<kNF>::kWarps, kWorkers = kPub ? kWarps - 1 : kWarps;
-    const size_t smem = Cfg<kNF>::kWarpSmem * kWarps;
+    constexpr int kWorkers = kPub ? kWarps - 1 : kWarps;
+    const size_t smem = kWarpSmem * kWarps;
     const long long ntasks = 8LL * a.nbricks * a.nfields_active;
-    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<kPub, kNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCEIK_CUDA(cudaFuncSetAttribute(sweep_bricks16_kernel<kPub>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<long long>((ntasks + kWorkers - 1) / kWorkers, nsm);
-    sweep_bricks16_kernel<kPub, kNF><<<grid, kWarps * 32, smem, st>>>(a);
+    sweep_bricks16_kernel<kPub><<<grid, kWarps * 32, smem, st>>>(a);
 }
 }  // namespace
 
@@ -647,13 +651,11 @@ void launch_iteration_bricks16(const BrickArgs &a, cudaStream_t st) {
     if (a.nfields_active == 0) return;
     if (a.zc < 1 || a.zc > kMaxZc || a.by != kBy || a.nx % kBx != 0) throw CudaError("bricks16: unsupported geometry");
     if (!a.slow_is_fh) throw CudaError("bricks16: expects the slowness premultiplied by h");
-    if (a.fields_per_task != 1 && a.fields_per_task != 2) throw CudaError("bricks16: 1 or 2 fields per task");
     int dev = 0, nsm = 0;
     MCEIK_CUDA(cudaGetDevice(&dev));
     MCEIK_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    if (a.fields_per_task == 2) launch_flavour<false, 2>(a, nsm, st);
-    else if (a.publisher) launch_flavour<true, 1>(a, nsm, st);
-    else launch_flavour<false, 1>(a, nsm, st);
+    if (a.publisher) launch_flavour<true>(a, nsm, st);
+    else launch_flavour<false>(a, nsm, st);
     MCEIK_LAUNCH_CHECK();
 }
 

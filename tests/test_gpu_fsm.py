@@ -94,12 +94,12 @@ def test_both_publication_flavours_of_the_brick_kernel(gpu_ctx, publisher):
     xs, ys, zs = cases.interior_sources(nf, nx, ny, nz, h, seed=4)
     ts = np.zeros(nf)
     ref, its = _oracle_fields(nx, ny, nz, h, slow, fmodel[:6], xs[:6], ys[:6], zs[:6], ts[:6], 1e-6, 20)
-    gpu_ctx.set_tuning("PUBLISHER", int(publisher)).set_tuning("PAIR_MIN", 0)
+    gpu_ctx.set_tuning("PUBLISHER", int(publisher))
     try:
         sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
         u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs)
     finally:
-        gpu_ctx.set_tuning("PUBLISHER", -1).set_tuning("PAIR_MIN", 24)
+        gpu_ctx.set_tuning("PUBLISHER", -1)
     assert not ferr.any()
     assert np.array_equal(iters[:6], its) and np.array_equal(u[:6], ref)
     # the remaining fields against the other flavour (default for this field count)
@@ -225,12 +225,10 @@ def test_homogeneous_tables(gpu_ctx):
 
 
 @pytest.mark.parametrize("natural", [0, 1])
-def test_two_fields_per_task(gpu_ctx, natural):
-    """The pair flavour of sweep_bricks16_kernel (two fields of one slowness model walk a brick together, forced here
-    from 2 active fields on): 9 fields over 2 models -- an odd count per model, so one task carries a single field
-    whose second copy is computed and never stored --, several sources in one field, a grid with partial bricks in y
-    and more than one brick along z; on the kernel's blocked layout (default) and on the caller's [z][y][x] layout.
-    Bit-equal to the oracle."""
+def test_blocked_and_natural_layouts(gpu_ctx, natural):
+    """sweep_bricks16_kernel on its blocked layout (default: 512-byte brick planes + x-face copies) and on the
+    caller's [z][y][x] layout: 9 fields over 2 models, several sources in one field, a grid with partial bricks in y
+    and more than one brick along z.  Bit-equal to the oracle."""
     from mceik_b200.eikonal import EikonalSolver
     nx, ny, nz, h = 40, 28, 300, 200.0
     n = nx * ny * nz
@@ -240,12 +238,12 @@ def test_two_fields_per_task(gpu_ctx, natural):
     xs, ys, zs = cases.interior_sources(nf + 1, nx, ny, nz, h, seed=12)
     src_ptr = np.array([0, 2] + list(range(3, nf + 2)), np.int32)  # field 0 has two sources
     ts = np.linspace(0.0, 0.5, nf + 1)
-    gpu_ctx.set_tuning("PAIR_MIN", 2).set_tuning("NATURAL", natural)
+    gpu_ctx.set_tuning("NATURAL", natural)
     try:
         sol = EikonalSolver(gpu_ctx, nx, ny, nz, h, tol=1e-6, maxit=20)
         u, _, iters, ferr = sol.solve_host(slow, fmodel, ts, xs, ys, zs, src_ptr=src_ptr)
     finally:
-        gpu_ctx.set_tuning("PAIR_MIN", 24).set_tuning("NATURAL", 0)
+        gpu_ctx.set_tuning("NATURAL", 0)
     assert not ferr.any()
     for f in range(nf):
         a, b = src_ptr[f], src_ptr[f + 1]
