@@ -203,6 +203,45 @@ int mceik_fsm_last_sweep_stats(mceik_ctx *ctx, double *sweep_ms, int *launches);
 int mceik_selftest_solver(mceik_ctx *ctx, unsigned long long seed, long long samples, long long *bad_sqrt,
                           long long *bad_solve);
 
+/*
+ * Multi-GPU (one process per GPU): the fields of a batched solve are shared out over the ranks of a communicator,
+ * every rank solves its fields without any communication, and one in-place NCCL all-gather over NVLink replicates
+ * the fp32 tables.  This replaces the reference's decomposition of ONE field over the ranks of an MPI communicator
+ * with a ghost exchange per sweep (eikonal3d_initialize / eikonal3d_solve, fsm3d.f90:1583-1840, communicators from
+ * mpiutils.f90:99-264): as there, the host hands in a communicator and nothing else.
+ *   mceik_comm_unique_id   rank 0 obtains the 128-byte NCCL id and distributes it with the host's own means
+ *                          (MPI_Bcast in the reference's drivers, torch.distributed in bench.py);
+ *   mceik_comm_init        every rank: joins (collective); mceik_comm_destroy leaves.
+ *   mceik_fsm_assign_fields  the deterministic assignment every rank computes: fields of a slowness model are dealt
+ *                          over the ranks holding that model, heaviest first when `cost` (e.g. the iteration counts of
+ *                          the previous solve of an MCMC loop; NULL = equal) is given.  table_row[f] = rank * slots + k.
+ *   mceik_fsm_solve_sharded_dev  collective.  All arguments describe ALL nfields fields and are identical on every
+ *                          rank (d_slow: every model resident on every rank).  d_tables_all [world * slots][ldtab]
+ *                          receives every field's fp32 table at row table_row[f] on every rank; iters / field_ierr
+ *                          [nfields] are filled on every rank.  Returns 1 when any field failed its boundary conditions.
+ *   mceik_tables_allgather the collective alone (in place: rank r's rows are [r * slots, (r + 1) * slots)).
+ * NCCL is loaded at run time (libnccl.so.2); without it these entry points return -2 and the rest of the library works.
+ */
+int mceik_comm_unique_id(void *id128);
+int mceik_comm_init(mceik_ctx *ctx, int world, int rank, const void *id128);
+int mceik_comm_destroy(mceik_ctx *ctx);
+int mceik_fsm_assign_fields(int nfields, const int *field_model, const int *cost, int world, int *rank_of_field,
+                            int *table_row, int *slots);
+int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow, int nfields,
+                                const int *field_model, const int *src_ptr, const double *ts, const double *xs,
+                                const double *ys, const double *zs, const int *cost, float *d_tables_all, size_t ldtab,
+                                int *iters, int *field_ierr, int *table_row);
+int mceik_tables_allgather(mceik_ctx *ctx, float *d_tables_all, size_t ldtab, int slots);
+
+/* Forward-loop misfit of many proposals (BASELINE config 5; the reference has no code for it, the definition is the
+ * build's): model m owns tables [m * ntab, (m + 1) * ntab) of d_tables [nmodels * ntab][ldgrd]; every
+ * event e sits at its catalogue node d_node[e] (0-based, < ngrd) with picks d_tobs / d_varobs / d_use [nevents][ntab]
+ * (use != 0: the pick counts); misfit[m] = sum_e sum_j (w_j/sqrt2 (tobs_j - (T_j + t0_e)))^2 with the analytic
+ * weighted-mean origin time t0_e of locate.c:399-410.  Device pointers, asynchronous on the context stream. */
+int mceik_catalog_misfit_dev(mceik_ctx *ctx, const float *d_tables, size_t ldgrd, int ngrd, int nmodels, int ntab, int nevents,
+                             const int *d_node, const double *d_tobs, const double *d_varobs, const int *d_use,
+                             double *d_misfit);
+
 /* Analytic homogeneous tables on the device: fp32 table t = dist/vel per station (homog.c:594-621
  * followed by homog.c:624-635).  d_tables [nstations][ldtab]; xs,ys,zs,vel are host arrays. */
 int mceik_homogeneous_tables_dev(mceik_ctx *ctx, int nx, int ny, int nz, double x0, double y0, double z0,

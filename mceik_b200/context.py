@@ -21,6 +21,22 @@ class Context:
         _lib.check(self._lib.mceik_fsm_set_tuning(self.handle, key.encode(), int(value)), "mceik_fsm_set_tuning")
         return self
 
+    @staticmethod
+    def comm_unique_id():
+        """``mceik_comm_unique_id``: the 128-byte NCCL id rank 0 hands to the other ranks (bytes)."""
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().mceik_comm_unique_id(buf), "mceik_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, world, rank, unique_id):
+        """``mceik_comm_init`` (collective): join the ranks that share the sources of a sharded solve."""
+        assert len(unique_id) == 128
+        _lib.check(self._lib.mceik_comm_init(self.handle, int(world), int(rank), C.c_char_p(bytes(unique_id))), "mceik_comm_init")
+        return self
+
+    def comm_destroy(self):
+        _lib.check(self._lib.mceik_comm_destroy(self.handle), "mceik_comm_destroy")
+
     def synchronize(self):
         _lib.check(self._lib.mceik_ctx_synchronize(self.handle), "mceik_ctx_synchronize")
 

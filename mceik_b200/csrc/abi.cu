@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/mceik_b200.h"
+#include "comm.cuh"
 #include "common.cuh"
 #include "fsm.cuh"
 #include "gs.cuh"
@@ -50,6 +51,7 @@ struct mceik_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fin = nullptr;
     // mceik_fsm_solve_batched_host with pinned output: a converged field is copied back on copy_stream while
     // the remaining fields keep iterating (early_u = host destination, early_done[f] = already on its way)
+    comm::Comm *comm = nullptr;  // mceik_comm_init: the ranks sharing the sources (one process per GPU)
     cudaStream_t copy_stream = nullptr;
     double *early_u = nullptr;
     std::vector<char> early_done;
@@ -70,7 +72,7 @@ struct mceik_ctx {
         int locate_no_align = 0;  // 1: keep ragged event blocks on the general search kernel (MCEIK_LOCATE_NO_ALIGN)
     } tune;
     // eikonal workspaces
-    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_ub, ws_u0b;
+    DevBuf ws_slow, ws_u, ws_u0, ws_tab, ws_meta, ws_ctrl, ws_lupd, ws_xyzv, ws_fh, ws_ub, ws_u0b, ws_comm;
     // locator state
     const float *d_tables = nullptr;
     DevBuf own_tables;
@@ -563,12 +565,13 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         cudaStreamSynchronize(c->stream);
         c->plan.release();
         c->bplan.release();
-        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh, &c->ws_ub, &c->ws_u0b,
+        for (DevBuf *b : {&c->ws_slow, &c->ws_u, &c->ws_u0, &c->ws_tab, &c->ws_meta, &c->ws_ctrl, &c->ws_lupd, &c->ws_xyzv, &c->ws_fh, &c->ws_ub, &c->ws_u0b, &c->ws_comm,
                           &c->own_tables, &c->ws_gs_in, &c->ws_gs_w, &c->ws_gs_part, &c->ws_gs_out, &c->ws_gs_misc})
             b->release();
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->ev_fin) cudaEventDestroy(c->ev_fin);
+        try { comm::destroy(c->comm); } catch (...) {}
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     } catch (...) {
@@ -691,6 +694,128 @@ int mceik_fsm_solve_batched_host(mceik_ctx *ctx, const mceik_fsm_grid *grid, int
             MCEIK_CUDA(cudaMemcpyAsync(tables, d_tab, sizeof(float) * ldtab * nfields, cudaMemcpyDeviceToHost, ctx->stream));
         MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
         return rc;
+    });
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: sources sharded over the ranks of a communicator, tables replicated (comm.cu)
+// ------------------------------------------------------------------------------------------
+int mceik_comm_unique_id(void *id128) {
+    return guarded([&]() -> int {
+        if (!id128) { set_error("mceik_comm_unique_id: NULL"); return -1; }
+        comm::unique_id(id128);
+        return 0;
+    });
+}
+
+int mceik_comm_init(mceik_ctx *ctx, int world, int rank, const void *id128) {
+    return guarded([&]() -> int {
+        if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) { set_error("mceik_comm_init: bad argument"); return -1; }
+        if (ctx->comm) { set_error("mceik_comm_init: the context already has a communicator"); return 1; }
+        DeviceGuard dg(ctx->device);
+        ctx->comm = comm::create(world, rank, id128);
+        return 0;
+    });
+}
+
+int mceik_comm_destroy(mceik_ctx *ctx) {
+    return guarded([&]() -> int {
+        if (!ctx) return -1;
+        DeviceGuard dg(ctx->device);
+        comm::destroy(ctx->comm);
+        ctx->comm = nullptr;
+        return 0;
+    });
+}
+
+int mceik_fsm_assign_fields(int nfields, const int *field_model, const int *cost, int world, int *rank_of_field, int *table_row,
+                            int *slots) {
+    return guarded([&]() -> int {
+        if (nfields < 0 || world < 1 || (nfields > 0 && !field_model)) { set_error("mceik_fsm_assign_fields: bad argument"); return -1; }
+        std::vector<int> rk, row;
+        int sl = 0;
+        comm::assign_fields(nfields, field_model, cost, world, rk, row, sl);
+        for (int f = 0; f < nfields; ++f) {
+            if (rank_of_field) rank_of_field[f] = rk[f];
+            if (table_row) table_row[f] = row[f];
+        }
+        if (slots) *slots = sl;
+        return 0;
+    });
+}
+
+int mceik_tables_allgather(mceik_ctx *ctx, float *d_tables_all, size_t ldtab, int slots) {
+    return guarded([&]() -> int {
+        if (!ctx || !d_tables_all || slots < 0) { set_error("mceik_tables_allgather: bad argument"); return -1; }
+        DeviceGuard dg(ctx->device);
+        comm::all_gather_inplace(ctx->comm, d_tables_all, sizeof(float) * ldtab * (size_t)slots, ctx->stream);
+        return 0;
+    });
+}
+
+int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int nmodels, const double *d_slow, int nfields,
+                                const int *field_model, const int *src_ptr, const double *ts, const double *xs, const double *ys,
+                                const double *zs, const int *cost, float *d_tables_all, size_t ldtab, int *iters, int *field_ierr,
+                                int *table_row) {
+    return guarded([&]() -> int {
+        if (!ctx || !grid || !d_slow || !field_model || !src_ptr || !d_tables_all || nfields < 0) {
+            set_error("mceik_fsm_solve_sharded_dev: bad argument");
+            return -1;
+        }
+        DeviceGuard dg(ctx->device);
+        const int world = comm::world(ctx->comm), rank = comm::rank(ctx->comm);
+        std::vector<int> rk, row;
+        int slots = 0;
+        comm::assign_fields(nfields, field_model, cost, world, rk, row, slots);
+        // this rank's fields, in increasing field order (= increasing table row)
+        std::vector<int> mine, fm, sp(1, 0);
+        std::vector<double> lts, lxs, lys, lzs;
+        for (int f = 0; f < nfields; ++f) {
+            if (rk[f] != rank) continue;
+            mine.push_back(f);
+            fm.push_back(field_model[f]);
+            for (int q = src_ptr[f]; q < src_ptr[f + 1]; ++q) { lts.push_back(ts[q]); lxs.push_back(xs[q]); lys.push_back(ys[q]); lzs.push_back(zs[q]); }
+            sp.push_back((int)lts.size());
+        }
+        const int nl = (int)mine.size();
+        std::vector<int> stat(2 * (size_t)slots * world, 0);  // per rank: [iters x slots][ierr x slots]
+        int *my = stat.data() + 2 * (size_t)slots * rank;
+        // the tables of the local fields land in this rank's rows of the replicated buffer
+        int rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nl, fm.data(), sp.data(), lts.data(), lxs.data(), lys.data(), lzs.data(), nullptr,
+                               d_tables_all + (size_t)rank * slots * ldtab, ldtab, my, my + slots);
+        if (rc < 0) return rc;
+        comm::all_gather_inplace(ctx->comm, d_tables_all, sizeof(float) * ldtab * (size_t)slots, ctx->stream);
+        if (world > 1) {  // iteration counts and error flags of every field, on every rank
+            int *d_stat = static_cast<int *>(ctx->ws_comm.ensure(sizeof(int) * stat.size()));
+            MCEIK_CUDA(cudaMemcpyAsync(d_stat + 2 * (size_t)slots * rank, my, sizeof(int) * 2 * slots, cudaMemcpyHostToDevice, ctx->stream));
+            comm::all_gather_inplace(ctx->comm, d_stat, sizeof(int) * 2 * (size_t)slots, ctx->stream);
+            MCEIK_CUDA(cudaMemcpyAsync(stat.data(), d_stat, sizeof(int) * stat.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        MCEIK_CUDA(cudaStreamSynchronize(ctx->stream));
+        int any = 0;
+        for (int f = 0; f < nfields; ++f) {
+            const int r = rk[f], pos = row[f] - r * slots;
+            if (iters) iters[f] = stat[2 * (size_t)slots * r + pos];
+            const int e = stat[2 * (size_t)slots * r + slots + pos];
+            if (field_ierr) field_ierr[f] = e;
+            any |= e;
+            if (table_row) table_row[f] = row[f];
+        }
+        return any ? 1 : 0;
+    });
+}
+
+int mceik_catalog_misfit_dev(mceik_ctx *ctx, const float *d_tables, size_t ldgrd, int ngrd, int nmodels, int ntab, int nevents,
+                             const int *d_node, const double *d_tobs, const double *d_varobs, const int *d_use, double *d_misfit) {
+    return guarded([&]() -> int {
+        if (!ctx || !d_tables || !d_node || !d_tobs || !d_varobs || !d_use || !d_misfit || nmodels < 0 || ntab < 1 || nevents < 0 ||
+            ngrd < 1 || ldgrd < (size_t)ngrd) {
+            set_error("mceik_catalog_misfit_dev: bad argument");
+            return -1;
+        }
+        DeviceGuard dg(ctx->device);
+        gs::launch_catalog_misfit(d_tables, ldgrd, nmodels, ntab, nevents, d_node, d_tobs, d_varobs, d_use, d_misfit, ctx->stream);
+        return 0;
     });
 }
 

@@ -517,6 +517,59 @@ __global__ void finalize_kernel(int nevents, int nlanes, const Partial *__restri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Catalogue misfit of many proposals (BASELINE config 5; no reference code -- the definition is SURVEY.md 8d C5):
+// for model m and event e at its catalogue node, with the model's own tables T_j = tables[m * ntab + j][node_e],
+//   w_j = 1 / var_j,  t0 = sum_j (w_j / sum w) (tobs_j - T_j),  obj_e = sum_j (w_j * sqrt(1/2) * (tobs_j - (T_j + t0)))^2
+// over the used picks in pick order (the arithmetic of locate.c:399-410, 500-513), misfit_m = sum_e obj_e.
+// One block per model, one thread per event (strided), then a fixed-order tree: bit-reproducible run to run.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) catalog_misfit_kernel(const float *__restrict__ tables, size_t ldgrd, int ntab, int nevents,
+                                                            const int *__restrict__ node, const double *__restrict__ tobs,
+                                                            const double *__restrict__ var, const int *__restrict__ use,
+                                                            double *__restrict__ out) {
+    const int m = blockIdx.x;
+    const float *tm = tables + (size_t)m * ntab * ldgrd;
+    __shared__ double part[256];
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < nevents; e += blockDim.x) {
+        const int g = node[e];
+        const double *to = tobs + (size_t)e * ntab, *va = var + (size_t)e * ntab;
+        const int *us = use + (size_t)e * ntab;
+        double xnorm = 0.0;
+        for (int j = 0; j < ntab; ++j)
+            if (us[j]) xnorm = __dadd_rn(xnorm, __ddiv_rn(1.0, va[j]));
+        double t0 = 0.0;
+        for (int j = 0; j < ntab; ++j)
+            if (us[j]) {
+                const double w = __ddiv_rn(__ddiv_rn(1.0, va[j]), xnorm);
+                t0 = __dadd_rn(t0, __dmul_rn(w, __dsub_rn(to[j], (double)tm[(size_t)j * ldgrd + g])));
+            }
+        double obj = 0.0;
+        for (int j = 0; j < ntab; ++j)
+            if (us[j]) {
+                const double w = __dmul_rn(__ddiv_rn(1.0, va[j]), 0.7071067811865475);
+                const double r = __dmul_rn(w, __dsub_rn(to[j], __dadd_rn((double)tm[(size_t)j * ldgrd + g], t0)));
+                obj = __dadd_rn(obj, __dmul_rn(r, r));
+            }
+        if (xnorm > 0.0) acc = __dadd_rn(acc, obj);  // an event without a usable pick contributes nothing
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) part[threadIdx.x] = __dadd_rn(part[threadIdx.x], part[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[m] = part[0];
+}
+
+void launch_catalog_misfit(const float *d_tables, size_t ldgrd, int nmodels, int ntab, int nevents, const int *d_node,
+                           const double *d_tobs, const double *d_var, const int *d_use, double *d_out, cudaStream_t st) {
+    if (nmodels == 0) return;
+    catalog_misfit_kernel<<<nmodels, 256, 0, st>>>(d_tables, ldgrd, ntab, nevents, d_node, d_tobs, d_var, d_use, d_out);
+    MCEIK_LAUNCH_CHECK();
+}
+
 void launch_finalize(int nevents, int nlanes, const Partial *d_partials, const int *d_nuse, int *d_iopt,
                      double *d_t0opt, double *d_objopt, cudaStream_t st) {
     if (nevents == 0) return;

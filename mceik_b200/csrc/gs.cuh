@@ -56,6 +56,10 @@ void launch_locate(const LocateArgs &a, cudaStream_t st);
 void launch_finalize(int nevents, int nlanes, const Partial *d_partials, const int *d_nuse, int *d_iopt,
                      double *d_t0opt, double *d_objopt, cudaStream_t st);
 
+// misfit of nmodels proposals against a catalogue located at fixed nodes (config 5), out[nmodels]
+void launch_catalog_misfit(const float *d_tables, size_t ldgrd, int nmodels, int ntab, int nevents, const int *d_node,
+                           const double *d_tobs, const double *d_var, const int *d_use, double *d_out, cudaStream_t st);
+
 // Single-event, full-grid outputs (the locate.c / gridsearch.f90 contract): t0[g], objfn[g].
 // ptr[j] is the row of used pick j in `test`; weights and corrected picks are already compressed.
 template <typename T>

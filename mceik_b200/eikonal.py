@@ -163,3 +163,25 @@ class EikonalSolver:
         _lib.check(rc, "mceik_fsm_solve_batched_dev")
         self.last_iters, self.last_ierr = iters, ferr
         return iters, ferr
+
+    def solve_sharded(self, d_slow, field_model, ts, xs, ys, zs, d_tables_all, cost=None, src_ptr=None):
+        """``mceik_fsm_solve_sharded_dev`` (collective over the context's communicator): all arguments describe ALL
+        fields and are the same on every rank; d_tables_all [world * slots, ldtab] fp32 receives every field's table
+        on every rank.  Returns (iters, ierr, table_row) for all fields."""
+        field_model = np.ascontiguousarray(field_model, dtype=np.int32)
+        nf = field_model.size
+        ts, xs, ys, zs, src_ptr = self._sources(nf, ts, xs, ys, zs, src_ptr)
+        assert d_slow.is_cuda and d_slow.is_contiguous() and d_slow.dtype.itemsize == 8 and d_slow.numel() % self.n == 0
+        assert d_tables_all.is_cuda and d_tables_all.is_contiguous() and d_tables_all.dtype.itemsize == 4
+        ldtab = d_tables_all.shape[-1]
+        iters, ferr, row = (np.zeros(nf, dtype=np.int32) for _ in range(3))
+        c = None if cost is None else np.ascontiguousarray(cost, dtype=np.int32)
+        self.lib.mceik_fsm_set_algo(self.ctx.handle, self.algo)
+        rc = self.lib.mceik_fsm_solve_sharded_dev(
+            self.ctx.handle, C.byref(self.grid), d_slow.numel() // self.n, C.c_void_p(d_slow.data_ptr()), nf,
+            _ptr(field_model, c_int_p), _ptr(src_ptr, c_int_p), _ptr(ts, c_dbl_p), _ptr(xs, c_dbl_p), _ptr(ys, c_dbl_p),
+            _ptr(zs, c_dbl_p), _ptr(c, c_int_p), C.c_void_p(d_tables_all.data_ptr()), ldtab, _ptr(iters, c_int_p),
+            _ptr(ferr, c_int_p), _ptr(row, c_int_p))
+        _lib.check(rc, "mceik_fsm_solve_sharded_dev")
+        self.last_iters, self.last_ierr = iters, ferr
+        return iters, ferr, row

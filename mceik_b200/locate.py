@@ -250,3 +250,15 @@ class Locator:
         if rc != 0:
             raise _lib.MceikError(f"mceik_locate_catalog rc={rc}: {_lib.last_error()}")
         return hypo[:4 * ne].reshape(ne, 4), iopt[:ne], obj[:ne]
+
+
+def catalog_misfit_device(ctx, d_tables, ngrd, nmodels, ntab, nevents, d_node, d_tobs, d_var, d_use, d_out):
+    """``mceik_catalog_misfit_dev`` (BASELINE config 5): misfit of ``nmodels`` proposals -- model m owns rows
+    [m*ntab, (m+1)*ntab) of the fp32 tables -- against a catalogue of ``nevents`` events at fixed nodes.  CUDA torch
+    tensors: d_node int32 [ne], d_tobs / d_var float64 [ne, ntab], d_use int32 [ne, ntab], d_out float64 [nmodels]."""
+    lib = _lib.load()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.mceik_catalog_misfit_dev(ctx.handle, p(d_tables), int(d_tables.shape[-1]), int(ngrd), int(nmodels), int(ntab),
+                                      int(nevents), p(d_node), p(d_tobs), p(d_var), p(d_use), p(d_out))
+    if rc != 0:
+        raise _lib.MceikError(f"mceik_catalog_misfit_dev rc={rc}: {_lib.last_error()}")

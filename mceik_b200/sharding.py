@@ -1,10 +1,12 @@
 """How the hot path shards over one-process-per-GPU ranks.
 
-* Eikonal fields (station x phase x model) are independent: contiguous blocks of fields per rank so
-  fields that share a slowness model sit together.  No communication during the solve (this
-  replaces the per-sweep ghost exchange of fsm3d.f90:971-1045).
-* After a source-sharded solve the packed fp32 tables are replicated with ONE all-gather so every
-  rank holds all tables for the locator.
+* Eikonal fields (station x phase x model) are independent: the library deals the fields of a slowness
+  model over the ranks that hold it (``assign_fields`` = ``mceik_fsm_assign_fields``), heaviest first when
+  the iteration counts of an earlier solve are known.  No communication during the solve (this replaces
+  the per-sweep ghost exchange of fsm3d.f90:971-1045).
+* Every rank writes its fp32 tables straight into its rows of the replicated table buffer and ONE in-place
+  NCCL all-gather completes it (``mceik_fsm_solve_sharded_dev``, csrc/comm.cu); the torch helpers below
+  are the gloo-testable mirror of that layout.
 * Events are independent: contiguous event ranges per rank, tables replicated, no data-path
   collective; the per-event results are gathered once at the end.
 
@@ -24,6 +26,22 @@ def shard_fields(nfields, world, rank):
     """Field indices solved by this rank."""
     lo, hi = block_range(nfields, world, rank)
     return np.arange(lo, hi, dtype=np.int64)
+
+
+def assign_fields(field_model, world, cost=None):
+    """``mceik_fsm_assign_fields``: (rank, table row, rows per rank) of every field -- fields of one slowness model
+    dealt over the ranks that hold it, heaviest first when a cost estimate (iteration counts of an earlier solve)
+    is given.  The same on every rank."""
+    import ctypes as C
+    from . import _lib
+    fm = np.ascontiguousarray(field_model, dtype=np.int32)
+    n = fm.size
+    rk, row, slots = np.zeros(n, np.int32), np.zeros(n, np.int32), C.c_int(0)
+    c = None if cost is None else np.ascontiguousarray(cost, dtype=np.int32)
+    p = lambda a: None if a is None else a.ctypes.data_as(_lib.c_int_p)
+    _lib.check(_lib.load().mceik_fsm_assign_fields(n, p(fm), p(c), int(world), p(rk), p(row), C.byref(slots)),
+               "mceik_fsm_assign_fields")
+    return rk, row, slots.value
 
 
 def shard_events(obs_ptr, world, rank):

@@ -92,6 +92,35 @@ def eikonal_serial(nx, ny, nz, h, slow, ts, xs, ys, zs, tol=1e-6, maxit=20, x0=0
     return u, e2, iters
 
 
+def eikonal_serial_timed(nx, ny, nz, h, slow, ts, xs, ys, zs, tol=1e-6, maxit=20):
+    """As eikonal_serial, timing job 2 (boundary conditions + sweeps) only -- the level structure of job 1 is built
+    once per grid by the reference's callers (fsm3d.f90:1985-1998).  Returns (u, ierr, iterations, seconds)."""
+    import time
+    L = lib()
+    slow = np.ascontiguousarray(slow, dtype=np.float64).ravel()
+    ts, xs, ys, zs = (np.ascontiguousarray(np.atleast_1d(a), dtype=np.float64) for a in (ts, xs, ys, zs))
+    u = np.empty(nx * ny * nz, dtype=np.float64)
+    ierr = C.c_int(0)
+    ci = lambda v: C.byref(C.c_int(v))
+    cd = lambda v: C.byref(C.c_double(v))
+
+    def call(job):
+        L.oracle_eikonal3d_serial_driver(ci(job), ci(0), ci(maxit), ci(len(ts)), ci(nx), ci(ny), ci(nz),
+                                         cd(tol), cd(h), cd(0.0), cd(0.0), cd(0.0),
+                                         _p(ts, c_dbl_p), _p(xs, c_dbl_p), _p(ys, c_dbl_p), _p(zs, c_dbl_p),
+                                         _p(slow, c_dbl_p), _p(u, c_dbl_p), C.byref(ierr))
+        return ierr.value
+
+    if call(1) != 0:
+        raise RuntimeError("oracle driver init failed")
+    t = time.perf_counter()
+    e2 = call(2)
+    dt = time.perf_counter() - t
+    iters = L.oracle_last_iterations()
+    call(3)
+    return u, e2, iters, dt
+
+
 def hamiltonian3d(a, b, c, f):
     L = lib()
     L.oracle_hamiltonian3d.restype = C.c_double

@@ -81,3 +81,43 @@ def test_c5_proposals_tables_and_misfit_stay_on_device(gpu_ctx):
         misfit.append(float(np.sum(d_obj.cpu().numpy())))
         misfit_ref.append(float(np.sum(obj_ref)))
     assert misfit == misfit_ref
+
+
+def test_c5_catalog_misfit_kernel(gpu_ctx):
+    """mceik_catalog_misfit_dev (config 5: misfit of every proposal against a catalogue at fixed nodes) against a
+    numpy statement of the same sums -- per event bit-equal arithmetic (locate.c:399-410, 500-513 order); the sum
+    over events uses a fixed tree, so the total is compared to 1e-12 relative."""
+    import torch
+    from mceik_b200.locate import catalog_misfit_device
+    rng = np.random.default_rng(31)
+    nmod, ntab, ne, ngrd = 5, 7, 300, 4000
+    tables = rng.uniform(0.5, 20.0, (nmod * ntab, ngrd)).astype(np.float32)
+    node = rng.integers(0, ngrd, ne).astype(np.int32)
+    tobs = rng.uniform(1.0, 25.0, (ne, ntab))
+    var = rng.choice(np.array([0.1, 0.25, 0.5]), (ne, ntab))
+    use = (rng.uniform(size=(ne, ntab)) >= 0.2).astype(np.int32)
+    use[3] = 0  # an event without picks contributes nothing
+    dev = lambda a: torch.from_numpy(a).cuda()
+    out = torch.empty(nmod, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    catalog_misfit_device(gpu_ctx, dev(tables), ngrd, nmod, ntab, ne, dev(node), dev(tobs), dev(var), dev(use), out)
+    gpu_ctx.synchronize()
+    got = out.cpu().numpy()
+    for m in range(nmod):
+        tot = 0.0
+        for e in range(ne):
+            T = tables[m * ntab:(m + 1) * ntab, node[e]].astype(np.float64)
+            xnorm, t0, obj = 0.0, 0.0, 0.0
+            for j in range(ntab):
+                if use[e, j]:
+                    xnorm += 1.0 / var[e, j]
+            for j in range(ntab):
+                if use[e, j]:
+                    t0 += ((1.0 / var[e, j]) / xnorm) * (tobs[e, j] - T[j])
+            for j in range(ntab):
+                if use[e, j]:
+                    r = ((1.0 / var[e, j]) * 0.7071067811865475) * (tobs[e, j] - (T[j] + t0))
+                    obj += r * r
+            if xnorm > 0:
+                tot += obj
+        assert abs(got[m] - tot) <= 1e-12 * abs(tot), (m, got[m], tot)

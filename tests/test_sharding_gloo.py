@@ -64,3 +64,34 @@ def test_gloo_world2_gathers(nfields, nevents):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+def test_field_assignment_of_the_c_abi():
+    """mceik_fsm_assign_fields (host logic, no GPU): every rank holds one slowness model when there are at least as
+    many ranks as models, fields are dealt evenly, a cost estimate balances the load (longest first), rows are
+    rank-major, and the answer is deterministic."""
+    import ctypes as C
+    from mceik_b200 import _lib, sharding
+    lib = _lib.load()
+    nf, world = 128, 8
+    fmodel = np.repeat(np.array([0, 1], np.int32), 64)
+    rk, row, slots = sharding.assign_fields(fmodel, world)
+    assert slots == 16 and np.all(np.bincount(rk, minlength=world) == 16)
+    assert set(rk[:64]) == {0, 1, 2, 3} and set(rk[64:]) == {4, 5, 6, 7}
+    assert sorted(row) == list(range(nf)) and np.all(row // slots == rk)
+    rng = np.random.default_rng(0)
+    cost = rng.integers(6, 11, nf).astype(np.int32)
+    rk2, row2, _ = sharding.assign_fields(fmodel, world, cost)
+    load = np.array([cost[rk2 == r].sum() for r in range(world)])
+    naive = np.array([cost[r * 16:(r + 1) * 16].sum() for r in range(world)])
+    assert load.max() - load.min() <= 2 and load.max() <= naive.max()
+    assert np.all(np.bincount(rk2, minlength=world) == 16)
+    rk3, row3, _ = sharding.assign_fields(fmodel, world, cost)
+    assert np.array_equal(rk2, rk3) and np.array_equal(row2, row3)
+    # more models than ranks, ragged counts
+    fm = np.array([0, 1, 2, 0, 1, 2, 2], np.int32)
+    rk4, row4, sl4 = sharding.assign_fields(fm, 2)
+    assert sl4 == 4 and np.bincount(rk4, minlength=2).max() <= 4 and len(set(row4)) == 7
+    # a single rank
+    rk5, row5, sl5 = sharding.assign_fields(fm, 1)
+    assert sl5 == 7 and not rk5.any() and list(row5) == list(range(7))

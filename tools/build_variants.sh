@@ -7,7 +7,7 @@ mkdir -p ../../build
 for v in "$@"; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
     -Xcompiler -fPIC,-ffp-contract=off -cudart static -DMCEIK_DBG=$v -shared -o ../../build/lib_dbg$v.so \
-    abi.cu fsm.cu fsm_bricks.cu fsm_bricks16.cu gs.cu &
+    abi.cu comm.cu fsm.cu fsm_bricks.cu fsm_bricks16.cu gs.cu -ldl &
 done
 wait
 ls -la ../../build/lib_dbg*.so
