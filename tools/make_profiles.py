@@ -21,7 +21,7 @@ for r in rows:
     d[1] += float(r[-1]) / 1e6
 total_ms = sum(v[1] for v in tot.values())
 with open(os.path.join(P, f"launches_{tag}.md"), "w") as f:
-    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 64`, N=1\n\n")
+    f.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 1024`, N=1\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (cold-cache, serialised launches: "
             "compare SHARES, not absolute times; the first 400 launches of the command).\n\n")
     f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
@@ -66,11 +66,23 @@ for rep, kern in (("prof_fsm.ncu-rep", "sweep_bricks16_kernel"), ("prof_gs.ncu-r
                   "duration_ms_under_ncu": float(m["gpu__time_duration.sum"][1]) * (1.0 if m["gpu__time_duration.sum"][0] == "ms" else 1e-3),
                   "units_per_launch": units_per_launch[kern],
                   "unit": "node-updates" if kern.startswith("sweep") else "events",
-                  "source": f"profiles/ncu_summary_{tag}.md ({rep}); command: python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 64"}
+                  "source": f"profiles/ncu_summary_{tag}.md ({rep}); command: python bench.py --steps 2 --warmup 1 --skip-cpu --fields 32 --gs-events 1024"}
     roof[kern]["dram_bytes_per_unit"] = roof[kern]["dram_bytes_per_launch"] / units_per_launch[kern]
     lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), path, "", "14"],
                            capture_output=True, text=True).stdout
     out.write("\nStall reasons and hottest source lines (warp-state sampling):\n\n```\n" + lines[lines.index("--- total samples"):] + "```\n")
+# ---- instruction mix of the sweep kernel: warp instructions per node-update and pipe
+pp = os.path.join(G, "pipes_fsm.csv")
+if os.path.exists(pp):
+    rows = [r for r in csv.reader(open(pp)) if len(r) > 10 and r[0].isdigit()]
+    upd = units_per_launch["sweep_bricks16_kernel"]
+    out.write(f"\n## Instruction mix of `sweep_bricks16_kernel` (one launch, {upd / 1e9:.2f} G node-updates)\n\n"
+              "Warp-level instructions executed per pipe (`smsp__inst_executed_pipe_*.sum`), per 64 node-updates (= one warp-step of the "
+              "brick walk) and per node-update (x 32 lanes / 64).  A pipe's share need not add up: an instruction can use two pipes.\n\n"
+              "| metric | total | per 64 updates | lane-instructions per update |\n|---|---:|---:|---:|\n")
+    for r in rows:
+        name, val = r[-3], float(r[-1].replace(",", ""))
+        out.write(f"| {name} | {val:.4g} | {val / upd * 64:.1f} | {val / upd * 32:.1f} |\n")
 out.close()
 json.dump(roof, open(os.path.join(P, "roofline.json"), "w"), indent=1)
 print(open(os.path.join(P, f"launches_{tag}.md")).read())
