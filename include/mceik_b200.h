@@ -187,7 +187,7 @@ int mceik_fsm_solve_batched_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
  * (CTA-per-16^3-tile kernel, fsm.cu) or LEVELS (one launch per hyperplane; cross-check path). */
 int mceik_fsm_set_algo(mceik_ctx *ctx, int algo);
 /* Development switches of the sweep / search kernels (none is needed in production: the defaults are the measured
- * best).  Keys: "ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "NATURAL", "BATCH", "TRACE",
+ * best).  Keys: "ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "NATURAL", "L2PF", "BATCH", "TRACE",
  * "STATS", "DEBUG", "LOCATE_NO_ALIGN" (DESIGN.md section 5).  A context reads MCEIK_FSM_<KEY> / MCEIK_LOCATE_NO_ALIGN
  * from the environment once, when it is created.  Returns 0, or -1 for an unknown key. */
 int mceik_fsm_set_tuning(mceik_ctx *ctx, const char *key, int value);

@@ -67,6 +67,7 @@ struct mceik_ctx {
         int publisher = -1;   // 0 / 1: force one publication flavour
         int no_stagger = 0;   // 1: one field group in the ticket order
         int natural = 0;      // 1: bricks16 works on the caller's [z][y][x] layout instead of the blocked one
+        int l2pf = 0;         // brick records bulk-prefetched into the L2 this many planes ahead (experiment; 0 = off)
         int batch = 0;        // sequential field batches (experiment)
         int trace = 0, stats = 0, debug = 0;
         int locate_no_align = 0;  // 1: keep ragged event blocks on the general search kernel (MCEIK_LOCATE_NO_ALIGN)
@@ -88,14 +89,14 @@ int *tuning_slot(mceik_ctx *c, const char *key) {
     struct { const char *name; int *p; } const tab[] = {
         {"ZC", &c->tune.zc}, {"BY", &c->tune.by}, {"NO16", &c->tune.no16}, {"PUBLISH", &c->tune.publish},
         {"PUBLISHER", &c->tune.publisher}, {"NO_STAGGER", &c->tune.no_stagger}, 
-        {"NATURAL", &c->tune.natural}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
+        {"NATURAL", &c->tune.natural}, {"L2PF", &c->tune.l2pf}, {"BATCH", &c->tune.batch}, {"TRACE", &c->tune.trace},
         {"STATS", &c->tune.stats}, {"DEBUG", &c->tune.debug}, {"LOCATE_NO_ALIGN", &c->tune.locate_no_align}};
     for (const auto &e : tab)
         if (strcmp(e.name, key) == 0) return e.p;
     return nullptr;
 }
 void tuning_from_env(mceik_ctx *c) {
-    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "NATURAL", "BATCH", "TRACE",
+    for (const char *k : {"ZC", "BY", "NO16", "PUBLISH", "PUBLISHER", "NO_STAGGER", "NATURAL", "L2PF", "BATCH", "TRACE",
                           "STATS", "DEBUG"}) {
         const std::string name = std::string("MCEIK_FSM_") + k;
         if (const char *e = getenv(name.c_str())) *tuning_slot(c, k) = atoi(e);
@@ -319,6 +320,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             a.h = g->h;
             a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
             a.u = d_w; a.blocked = blocked ? 1 : 0;
+            a.l2_prefetch = ctx->tune.l2pf;
             a.brick_order = ctx->bplan.brick_order.as<int>();
             a.blevel_ptr = ctx->bplan.blevel_ptr.as<int>();
             a.queue = reinterpret_cast<unsigned long long *>(ctrl);

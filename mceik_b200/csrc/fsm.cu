@@ -329,7 +329,6 @@ void launch_iteration_tiles(const SweepArgs &a, cudaStream_t st) {
 // Tile plan
 // ------------------------------------------------------------------------------------------
 void TilePlan::build(int nx_, int ny_, int nz_, cudaStream_t st) {
-    static bool lvl_uploaded = false;
     if (nx_ == nx && ny_ == ny && nz_ == nz && ntiles > 0) return;
     nx = nx_; ny = ny_; nz = nz_;
     ntx = (nx + kTile - 1) / kTile;
@@ -369,11 +368,9 @@ void TilePlan::build(int nx_, int ny_, int nz_, cudaStream_t st) {
     lptr[kTileLevels] = (int)nodes.size();
     MCEIK_CUDA(cudaMemcpyAsync(lvl_nodes.ensure(sizeof(uint16_t) * kTileNodes), nodes.data(),
                                sizeof(uint16_t) * kTileNodes, cudaMemcpyHostToDevice, st));
-    if (!lvl_uploaded) {
-        MCEIK_CUDA(cudaMemcpyToSymbolAsync(c_lvl_ptr, lptr.data(), sizeof(int) * (kTileLevels + 1), 0,
-                                           cudaMemcpyHostToDevice, st));
-        lvl_uploaded = true;
-    }
+    // constant memory is per device and a plan is per context (= per device): upload with every (re)build
+    MCEIK_CUDA(cudaMemcpyToSymbolAsync(c_lvl_ptr, lptr.data(), sizeof(int) * (kTileLevels + 1), 0,
+                                       cudaMemcpyHostToDevice, st));
     MCEIK_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
 }
 

@@ -97,6 +97,7 @@ struct BrickArgs {
     // neighbours read as their halo instead of 8 separate sectors of u; slow is [model][brick column][z][64].  Rows
     // beyond ny hold u_nan.  launch_block_fields / launch_unblock_fields convert from / to the [z][y][x] layout.
     int blocked;
+    int l2_prefetch;              // bricks16 experiment (MCEIK_FSM_L2PF): brick records bulk-prefetched into the L2 this many planes ahead
     int batch;                    // bricks16 experiment (MCEIK_FSM_BATCH): > 0 = fields run in sequential batches of this size
     int publisher;                // bricks16: 1 = the last warp of every CTA publishes progress for the others
     const int *bc_ptr;            // [nfields+1] CSR into bc_node

@@ -88,6 +88,11 @@ __device__ __forceinline__ void cp_async8_if(bool p, void *smem_dst, const void 
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 8; }" ::"r"(s), "l"(gsrc), "r"((int)p) : "memory");
 }
+// TMA-family experiment (MCEIK_FSM_L2PF = planes ahead; 0 = off, the default): one lane asks the L2 for whole brick
+// records ahead of the ring's own copies with a bulk prefetch
+__device__ __forceinline__ void bulk_prefetch_l2(const void *g, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -430,6 +435,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             // face plane stored in step l: plane l - fl_lag; zo stands at (l + 7 - kofs_t) planes when the stores are issued
             bu_fl[fi] = reinterpret_cast<char *>(pu_fl[fi]) + (long long)(kofs_t - 7 - fl_lag) * zsb;
         }
+#ifdef MCEIK_B16_L2PF  // measured 4 % slower (profiles/kernel_evolution_r2.md): compiled in only for the experiment
+        const int pf_planes = blocked ? a.l2_prefetch : 0;
+#else
+        constexpr int pf_planes = 0;
+#endif
+        const double *rec0 = ufs[0] + (col * nz + zb) * kRec, *srec0 = sl + (col * nz + zb) * (kBx * kBy);
         auto issue_slot = [&](auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
             double *sp = U + ld_slot;
@@ -439,6 +450,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
 #pragma unroll
                 for (int fi = 0; fi < kNF; ++fi) cp_async16(sp + fi * kUCells + cu_t, bu_t[fi] + zo);
                 cp_async16(sp + cf_t, bf_t + zos);
+                if (pf_planes > 0 && lane == 0) {
+                    const int kp = ld_m + pf_planes;  // plane (in sweep order) the prefetch asks for
+                    if (kp < ez) {
+                        bulk_prefetch_l2(rec0 + (long long)kp * zstride, kRec * 8);
+                        bulk_prefetch_l2(srec0 + (long long)kp * szstride, kBx * kBy * 8);
+                    }
+                }
             } else if (k >= -1 && k <= ez) {  // rows beyond ey are loaded too: row ey is the clamped / downwind halo
                 const int kc = min(max(k, klo), khi);
 #pragma unroll
