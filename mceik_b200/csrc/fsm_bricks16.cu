@@ -1,28 +1,28 @@
-// fsm_bricks16.cu -- the streaming brick sweep kernel for grids with nx % 8 == 0 (sm_100a).
+// fsm_bricks16.cu -- the streaming brick sweep kernel for grids with nx % 8 == 0 (sm_100a): the default sweep path.
 //
-// Same algorithm, ring and scheduling as sweep_bricks_kernel (fsm_bricks.cu -- read its header
-// first); what changes is how the ring is fed and drained:
+// Same algorithm, skewed ring and scheduling as sweep_bricks_kernel (fsm_bricks.cu -- read its header first: a warp
+// walks one 8 x 8 x zc brick of one field for one sweep, one brick hyperplane per step); what differs is the data path:
 //
-//   * every global <-> shared transfer moves a PAIR of x-adjacent nodes (16 bytes): cp.async.cg
-//     (L2 only -- no L1 line is allocated, so the 200+ KB of shared memory the rings take do not
-//     starve the copies of L1) and 128-bit stores.  3 copies and 1 store per lane and step instead
-//     of 5 and 2.
-//   * a ring row keeps the brick's x order of MEMORY (column q = x - x_lo at index q + 2, halo pairs
-//     (-2,-1) and (8,9) at indices 0..1 and 10..11), whatever the sweep direction, so pairs land in
-//     order; the sweep direction only decides which of the two x-neighbours is "upwind" and which
-//     slot it lives in.  Rows (y) and planes (z) stay in sweep order.
-//
-//   * steps in which every transfer, update and store touches in-brick nodes run in whole publication chunks
-//     with all global addresses formed as (per-task byte base) + (one running plane offset);
-//   * a warp waits for its upwind x neighbour By - 2 steps less than for its upwind y neighbour, remembers the
-//     progress it has already observed and looks one chunk ahead;
+//   * the fields live in a BLOCKED layout while they are solved (BrickArgs::blocked, fsm.cuh): [brick column][z][80]
+//     = the 64 nodes of a brick plane (512 contiguous bytes) + copies of its columns 0 and 7.  A brick walk of the
+//     caller's [z][y][x] layout reads 64-byte pieces at a 2 KB stride, which the DRAM serves at 4.4 TB/s at most, and
+//     pays 8 sectors per side and plane for its x halo; here the walk is sequential and the x halo is the neighbour's
+//     face copy.  The kernel keeps the copies up to date itself (face staging ring FB, one 64-byte store per plane
+//     and side).  The [z][y][x] layout remains available (blocked = 0; tuning key NATURAL).
+//   * every global <-> shared transfer of nodes moves a PAIR of x-adjacent nodes (16 bytes): cp.async.cg (L2 only)
+//     and 128-bit stores -- 2 copies + 1 halo copy (24 lanes) + 1 store per lane and step.
+//   * a ring row keeps the brick's x order of MEMORY (column q = x - x_lo at cell q + 2 of a 10-cell row), whatever
+//     the sweep direction, so pairs land in order; the sweep direction only decides which of the two x-neighbours is
+//     "upwind" and which slot it lives in.  Rows (y) and planes (z) stay in sweep order.
+//   * steps in which every transfer, update and store touches in-brick nodes run in whole publication chunks with all
+//     global addresses formed as (per-task byte base) + (one running plane offset) and predicated halo copies;
+//   * a warp remembers the progress of its upwind neighbours it has already observed and looks one chunk ahead;
 //   * tickets interleave two groups of fields half a sweep apart (decode_ticket, fsm.cuh);
 //   * with few active fields the kernel runs in its publisher flavour (template parameter): the last warp of
 //     the CTA executes the gpu-scope fences and progress stores for the others.
 //
-// nx % 8 == 0 makes every brick full in x and every pair 16-byte aligned; other grids use
-// sweep_bricks_kernel.  Bricks at the grid's x faces fetch their clamped halo column (a copy of the
-// boundary column itself, fsm3d.f90:495-499) with an 8-byte cp.async.
+// nx % 8 == 0 makes every brick full in x and every pair 16-byte aligned; other grids use sweep_bricks_kernel.
+// What limits this kernel and everything that was tried: DESIGN.md section 4.1, profiles/kernel_evolution_r2.md.
 #include <algorithm>
 #include <type_traits>
 #include <vector>
