@@ -316,7 +316,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             // few fields: short publication interval (tight pipelining of the brick wavefront);
             // many fields: parallelism is plentiful, publish less often (each publication costs a fence)
             a.publish = active.size() >= 48 ? 16 : (active.size() > 16 ? 8 : 4);  // measured, profiles/kernel_evolution_r1.md
-            if (ctx->tune.publish > 0) a.publish = ctx->tune.publish;
+            if (ctx->tune.publish >= 2 && (ctx->tune.publish & (ctx->tune.publish - 1)) == 0) a.publish = ctx->tune.publish;  // a power of two
             a.h = g->h;
             a.active = d_active; a.field_model = d_fmodel; a.slow = bricks16 ? d_fh : d_slow; a.slow_is_fh = bricks16 ? 1 : 0;
             a.u = d_w; a.blocked = blocked ? 1 : 0;
@@ -394,10 +394,13 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
                                    cudaMemcpyDeviceToHost, st));
         MCEIK_CUDA(cudaStreamSynchronize(st));
         if (bricks && ctx->tune.stats) {
-            unsigned long long hs[4];
+            unsigned long long hs[8];
             MCEIK_CUDA(cudaMemcpy(hs, ctrl + 64, sizeof(hs), cudaMemcpyDeviceToHost));
             if (hs[3]) printf("[fsm stats] iter %d: tasks %llu  avg cycles: start-wait %.0f  upwind-wait %.0f  run %.0f\n", k, hs[3],
                               (double)hs[0] / hs[3], (double)hs[1] / hs[3], (double)hs[2] / hs[3]);
+            if (hs[3] && hs[4])  // -DMCEIK_B16_PROFILE builds: phases of a step, cycles per task
+                printf("[fsm stats]   step phases per task: issue %.0f  copy-wait+sync %.0f  reads+solve+writes %.0f  write-back %.0f\n",
+                       (double)hs[4] / hs[3], (double)hs[5] / hs[3], (double)hs[6] / hs[3], (double)hs[7] / hs[3]);
         }
         if (ctx->fsm_algo != MCEIK_FSM_ALGO_LEVELS) {
             float ms = 0.f;

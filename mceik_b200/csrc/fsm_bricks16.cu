@@ -53,7 +53,7 @@ constexpr int kFRow = 10;                          // slowness tile: row stride 
 constexpr int kFCells = kFRow * kBy;
 constexpr int kMaxZc = 256;
 constexpr int kProgShift = 12;
-constexpr int kLead = kBy + 3;
+constexpr int kLead = kBy + 4;                     // a slot is stored 4 steps after it was entered: slot m + By is in memory once m + By + 5 steps are done
 constexpr int kRec = kBx * kBy + 2 * kBy;          // blocked layout: doubles per brick plane (64 nodes + the two x-face copies)
 constexpr int kFacePlanes = 16;                    // planes of the face staging ring (a plane is written over 9 steps, stored the step after)
 constexpr int kBcMax = 16;                         // planes of one brick that hold boundary-condition nodes of one field
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
                 // Blocked layout: the x-halo comes from the neighbour's face copies, written one whole plane at a
-                // time 15 steps after the plane was entered: x needs 2 steps MORE lead than y.
+                // time 16 steps after the plane was entered: x needs 2 steps MORE lead than y.
                 const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? -2 : kBy - 2) : 0);
                 seen = max(seen, ahead);
                 if (seen < need)
@@ -395,12 +395,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         }
         // blocked: values of memory columns 0 and 7 go to the face staging FB[field][side][plane & 15][row] when their
         // pair is written back, and a whole plane of a side (64 contiguous bytes of the record) is stored the step
-        // after its 8 rows are in (so the step's own __syncwarp orders it): 14 steps after the plane was entered for
-        // the side of sweep column 0, 15 for sweep column 7
+        // after its 8 rows are in (so the step's own __syncwarp orders it): 15 steps after the plane was entered for
+        // the side of sweep column 0, 16 for sweep column 7
         const bool face_lane = blocked && (tp == 0 || tp == 3) && act_t;
         const int fb_t = (tp == 0 ? 0 : 1) * (kFacePlanes * kBy) + (yt - y_lo);  // + (plane & 15) * kBy + fi * 2 * kFacePlanes * kBy
         const int fl_side = (lane >> 2) & 1, fl_pair = lane & 3;                 // flush lanes 0..7: side, pair of rows
-        const int fl_lag = ((fl_side == 0) == !revx) ? 14 : 15;                  // memory column 0 is sweep column 0 unless revx
+        const int fl_lag = ((fl_side == 0) == !revx) ? 15 : 16;                  // memory column 0 is sweep column 0 unless revx
         const size_t fl_off = (col * nz + zb) * kRec + kBx * kBy + fl_side * kBy + 2 * fl_pair;
         if (blocked && ey < kBy) {  // rows outside the grid are never written: keep their face entries at u_nan
             for (int e = lane; e < kFaceCells; e += 32) FB[e] = DBL_MAX;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         for (int fi = 0; fi < kNF; ++fi) {
             bu_t[fi] = reinterpret_cast<const char *>(pu_t[fi]);
             bu_h[fi] = reinterpret_cast<const char *>(pu_h[fi]) + (long long)(kofs_t - kofs_h) * zsb;  // halo transfer of the same issue
-            bu_st[fi] = reinterpret_cast<char *>(pu_t[fi]) - (8 + kPrefetch) * zsb;  // pair written back in the same step (plane l - 3)
+            bu_st[fi] = reinterpret_cast<char *>(pu_t[fi]) - (9 + kPrefetch) * zsb;  // pair written back in the same step (slot l - 4)
             // face plane stored in step l: plane l - fl_lag; zo stands at (l + 7 - kofs_t) planes when the stores are issued
             bu_fl[fi] = reinterpret_cast<char *>(pu_fl[fi]) + (long long)(kofs_t - 7 - fl_lag) * zsb;
         }
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         int oc = ((mc % kRing) + kRing) % kRing * kSlot;
         int om = (oc == 0) ? (kRing - 1) * kSlot : oc - kSlot;
         int op = (oc + kSlot == kRing * kSlot) ? 0 : oc + kSlot;
-        int st_slot = ((-3 % kRing) + kRing) % kRing * kSlot;
+        int st_slot = ((-4 % kRing) + kRing) % kRing * kSlot;
 
         cp_async_wait<kPrefetch - 1>();
         __syncwarp();
@@ -517,12 +517,27 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             }
         }
 
-        const int nsteps = ez + kBy + 6 + (blocked ? 1 : 0);  // blocked: one more step stores the last face plane
+        const int nsteps = ez + kBy + 7 + (blocked ? 1 : 0);  // blocked: one more step stores the last face plane
+#ifdef MCEIK_B16_PROFILE  // step-phase cycle counters (lane 0): issue | copy wait + syncwarp | reads + solve + writes | write-back
+        long long ph[4] = {0, 0, 0, 0};
+#define MCEIK_PH(i) do { const long long t_ = clock64(); ph[i] += t_ - tph; tph = t_; } while (0)
+        long long tph = clock64();
+#else
+#define MCEIK_PH(i) do { } while (0)
+#endif
+        // One step = one brick hyperplane.  A single __syncwarp per step: after it the copies of slots <= l + 4 have landed
+        // for every lane and the results of step l - 1 are visible.  Everything else of the step is one region the compiler
+        // can interleave with the update chain: the neighbour reads, the write-back of slot l - 4 (final since step l - 1),
+        // the copies of slot l + 6 (they overwrite slot l - 5, last read in step l - 1) and the face plane completed in
+        // step l - 1.
         auto step_core = [&](int l, auto steady_tag) {
             constexpr bool kSteady = decltype(steady_tag)::value;
-            issue_slot(steady_tag);
-            cp_async_wait<kPrefetch>();
+#ifdef MCEIK_B16_PROFILE
+            tph = clock64();
+#endif
+            cp_async_wait<kPrefetch - 1>();
             __syncwarp();
+            MCEIK_PH(0);
 
             const int k0 = l - li - j0;
             bool go[kNQ];
@@ -559,6 +574,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                     fh[q] = U[oc + cf0 + c * kFRow];  // slow(ijk)*h (fsm3d.f90:470), multiplied once per solve (scale_slowness)
                 }
             }
+
+            // slot l - 4 is final: its pair of this lane goes back (one 16-byte store per field); lanes 0..7 also store the
+            // face plane whose last row arrived in the previous step
+            const int ks = l - 4 - kofs_t, kf = l - fl_lag;
+            const bool st_pair = !(kDbg & 8) && (kSteady || (act_t && (unsigned)ks < (unsigned)ez));
+            const bool st_face = blocked && lane < 8 && !(kDbg & 8) && (kSteady || (unsigned)kf < (unsigned)ez);
+            double2 wb[kNF], wf[kNF];
+#pragma unroll
+            for (int fi = 0; fi < kNF; ++fi) {
+                wb[fi] = wf[fi] = make_double2(0.0, 0.0);
+                if (st_pair) wb[fi] = *reinterpret_cast<const double2 *>(U + st_slot + fi * kUCells + cu_t);
+                if (st_face) wf[fi] = *reinterpret_cast<const double2 *>(FB + fi * 2 * kFacePlanes * kBy + fl_side * (kFacePlanes * kBy) +
+                                                                          (kf & (kFacePlanes - 1)) * kBy + 2 * fl_pair);
+            }
+            issue_slot(steady_tag);  // zo now stands at (l + 7 - kofs_t) planes
+#pragma unroll
+            for (int fi = 0; fi < kNF; ++fi) {
+                if (st_pair) {
+                    if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st[fi] + zo), wb[fi]);
+                    else __stcg(reinterpret_cast<double2 *>(pu_t[fi] + (long long)ks * zstride), wb[fi]);
+                    if (face_lane) FB[fi * 2 * kFacePlanes * kBy + fb_t + (ks & (kFacePlanes - 1)) * kBy] = tp == 0 ? wb[fi].x : wb[fi].y;
+                }
+                if (st_face) {
+                    if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_fl[fi] + zo), wf[fi]);
+                    else __stcg(reinterpret_cast<double2 *>(pu_fl[fi] + (long long)kf * zstride), wf[fi]);
+                }
+            }
+            MCEIK_PH(1);
+
             if (kDbg & 1) {
 #pragma unroll
                 for (int q = 0; q < kNQ; ++q) nv[q] = __dadd_rn(__dadd_rn(ux[q], uy[q]), __dadd_rn(uz[q], fh[q]));
@@ -576,36 +620,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                     self[q] = zp[q];
                 }
             }
-            __syncwarp();
-
-            // slot l - 3 is final: write its pair of this lane back (one 16-byte store per field)
-            {
-                const int ks = l - 3 - kofs_t;
-                if (!(kDbg & 8) && (kSteady || (act_t && (unsigned)ks < (unsigned)ez))) {
-#pragma unroll
-                    for (int fi = 0; fi < kNF; ++fi) {
-                        const double2 v = *reinterpret_cast<const double2 *>(U + st_slot + fi * kUCells + cu_t);
-                        if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_st[fi] + zo), v);
-                        else __stcg(reinterpret_cast<double2 *>(pu_t[fi] + (long long)ks * zstride), v);
-                        if (face_lane) FB[fi * 2 * kFacePlanes * kBy + fb_t + (ks & (kFacePlanes - 1)) * kBy] = tp == 0 ? v.x : v.y;
-                    }
-                }
-                if (blocked) {  // lanes 0..7: the face plane whose last row arrived in the previous step
-                    const int kf = l - fl_lag;
-                    if (lane < 8 && !(kDbg & 8) && (kSteady || (unsigned)kf < (unsigned)ez)) {
-#pragma unroll
-                        for (int fi = 0; fi < kNF; ++fi) {
-                            const double2 v = *reinterpret_cast<const double2 *>(FB + fi * 2 * kFacePlanes * kBy + fl_side * (kFacePlanes * kBy) +
-                                                                                 (kf & (kFacePlanes - 1)) * kBy + 2 * fl_pair);
-                            if (kSteady) __stcg(reinterpret_cast<double2 *>(bu_fl[fi] + zo), v);
-                            else __stcg(reinterpret_cast<double2 *>(pu_fl[fi] + (long long)kf * zstride), v);
-                        }
-                    }
-                }
-            }
+            MCEIK_PH(2);
             om = oc; oc = op;
             op = (op + kSlot == kRing * kSlot) ? 0 : op + kSlot;
             st_slot = (st_slot + kSlot == kRing * kSlot) ? 0 : st_slot + kSlot;
+            MCEIK_PH(3);
         };
         // progress of the brick is published (and the upwind bricks' progress awaited) every `publish` steps
         auto wait_chunk = [&](int l) { wait_upwind(l + publish + 4 + kPrefetch + kLead); };
@@ -624,7 +643,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         // brick that is not on the grid's x faces and holds no boundary-condition node; it runs in whole
         // publication chunks with no per-step bookkeeping
         const bool full = ey == kBy && !hasbc;
-        int s_lo = (kBy + 6 + publish - 1) & ~(publish - 1), s_hi = (ez - 3 - kPrefetch) & ~(publish - 1);
+        // (the pair stored in a steady step, plane l - 15 at least, and the face plane, l - 16, must exist)
+        int s_lo = (kBy + 8 + publish - 1) & ~(publish - 1), s_hi = (ez - 3 - kPrefetch) & ~(publish - 1);
         if (!full || s_hi <= s_lo) s_lo = s_hi = nsteps;
         int l = 0;
         for (; l < s_lo; ++l) step(l);
@@ -639,6 +659,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
         __syncwarp();
         if (lane == 0) publish_progress(done_f + brick, (s + 1) << kProgShift);
         __syncwarp();
+#ifdef MCEIK_B16_PROFILE
+        if (a.stats && lane == 0)
+            for (int i = 0; i < 4; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)ph[i]);
+#endif
         if (a.stats && lane == 0) {
             const long long t_end = clock64();
             atomicAdd(a.stats + 0, (unsigned long long)(t_deps - t_start));

@@ -8,9 +8,11 @@
  *   - cell (i,j,k), i in [-1,8], j in [-1,ey], k in [-1,ez], belongs to ring slot
  *     m = xgroup(i) + (j+1) + (k+1); slot m is LOADED from global memory (halo cells outside the grid
  *     clamped to the boundary node) when step m - 6 starts -- long before it is used -- and the in-brick
- *     cells of slot l - 3 are STORED at the end of step l;
- *   - a brick may load slot m only when its upwind y neighbour has completed m + By + 4 steps and its
- *     upwind x neighbour m + 6 (the fine-grained dependencies of the kernel), and starts only after its
+ *     cells of slot l - 4 (final since step l - 1) are STORED in step l;
+ *   - a brick may load slot m only when its upwind y neighbour has completed m + By + 5 steps and its
+ *     upwind x neighbour m + 7 (the fine-grained dependencies of the kernel on the [z][y][x] layout; on the
+ *     blocked layout the x halo comes from face copies stored later and the kernel asks for m + By + 7),
+ *     and starts only after its
  *     upwind z neighbour has finished;
  *   - the 8 sweeps of an iteration OVERLAP as in the kernel: a brick starts sweep s as soon as it and its six face
  *     neighbours have completed sweep s - 1 (and its upwind z neighbour sweep s), while other bricks are still in
@@ -180,11 +182,11 @@ static void step(brick_t *b)
             const double ubar = oracle_hamiltonian3d(ux, uy, uz, slow[g] * h, &ierr);
             if (ubar < self) { b->L[LIDX(b, i, j, k)] = ubar; b->changed = 1; }
         }
-    /* write back the in-brick cells of slot l - 3 */
+    /* write back the in-brick cells of slot l - 4 */
     for (int k = 0; k < b->ez; k++)
         for (int j = 0; j < b->ey; j++)
             for (int i = 0; i < BX; i++)
-                if (xgroup(i) + (j + 1) + (k + 1) == l - 3) u[gnode(b, i, j, k)] = b->L[LIDX(b, i, j, k)];
+                if (xgroup(i) + (j + 1) + (k + 1) == l - 4) u[gnode(b, i, j, k)] = b->L[LIDX(b, i, j, k)];
     b->progress = l + 1;
 }
 
@@ -196,7 +198,7 @@ static long iteration(brick_t *bk, long nb, unsigned *rng)
         *rng = *rng * 1664525u + 1013904223u;
         brick_t *b = bk + (*rng >> 8) % nb;
         if (b->sweep == 8) continue;
-        const int nsteps = b->ez + BY + 6;
+        const int nsteps = b->ez + BY + 7;
         int moved = 0;
         if (b->loaded < 0) {  /* start of a sweep: slots 0 .. AHEAD-1 */
             const int sk = (skip_mode && may_start(bk, b)) ? may_skip(bk, b) : 0;
@@ -233,7 +235,7 @@ int main(int argc, char **argv)
     unsigned rng = argc > 5 ? (unsigned)atoi(argv[5]) : 1u;
     const int dlead = argc > 6 ? atoi(argv[6]) : 0;
     skip_mode = argc > 7 ? atoi(argv[7]) : 0;
-    lead_x = 6 + dlead; lead_y = BY + 4 + dlead;
+    lead_x = 7 + dlead; lead_y = BY + 5 + dlead;
     if (nx % BX) { printf("nx must be a multiple of 8\n"); return 2; }
     nxy = (long)nx * ny;
     long n = nxy * nz;

@@ -203,7 +203,7 @@ def brick_emu(tmp_path_factory):
                                   (8, 8, 30, 16, 5), (40, 17, 33, 32, 6)])
 def test_brick_pipeline_schedule_reproduces_the_reference_order(brick_emu, args):
     """tests/brick_pipeline_emulation.c: the streaming brick schedule of fsm_bricks16.cu (ring slots loaded 6 steps
-    ahead, write-back 3 steps behind, upwind y neighbour By + 4 and x neighbour 6 steps ahead, random interleaving of
+    ahead, write-back 4 steps behind, upwind y neighbour By + 5 and x neighbour 7 steps ahead, random interleaving of
     the bricks) gives the reference-ordered oracle bit for bit and stays inside the 11-slot ring."""
     out = subprocess.run([brick_emu] + [str(a) for a in args], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("MATCH"), out.stdout
