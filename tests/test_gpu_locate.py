@@ -348,6 +348,39 @@ def test_catalog_struct_entry(gpu_ctx):
     assert np.array_equal(iopt, cat["true_node"])
     assert np.allclose(hypo[:, 3], cat["tori"], atol=1e-5)
     assert np.array_equal(hypo[:, 0], X[iopt].astype(np.float64))
+    # ... and a ragged, noisy catalogue (CSR obsPtr: every event its own pick list, unused picks, both jobs) against
+    # the oracle event by event: located node, objective and hypo = (x, y, z, t0) bit for bit
+    rng = np.random.default_rng(41)
+    ne, ntab = 19, tables.shape[0]
+    obs_ptr, stat, ptype, use, tob, var = [0], [], [], [], [], []
+    tori = rng.uniform(0, 5, ne)
+    for e in range(ne):
+        k = int(rng.integers(1, ntab + 1))
+        node = int(rng.integers(0, ngrd))
+        for t in rng.permutation(ntab)[:k]:
+            stat.append(t // 2 + 1)
+            ptype.append(t % 2 + 1)
+            use.append(int(rng.random() > 0.2))
+            corr = pcorr[t // 2] if t % 2 == 0 else scorr[t // 2]
+            tob.append(float(tables[t, node]) + tori[e] + corr + rng.normal(0, 0.03))
+            var.append(float(rng.choice([0.1, 0.25, 0.5])))
+        obs_ptr.append(len(stat))
+    obs_ptr = np.array(obs_ptr, np.int32)
+    stat, ptype, use = np.array(stat, np.int32), np.array(ptype, np.int32), np.array(use, np.int32)
+    tob, var = np.array(tob), np.array(var)
+    catalog = dict(nevents=ne, tori=tori, tobs=tob, varObs=var, luseObs=use, pickType=ptype, statPtr=stat, obsPtr=obs_ptr)
+    for job in (2, 1):
+        hypo, iopt, obj = loc.locate_catalog(catalog, stations, job)
+        for e in range(ne):
+            b, en = obs_ptr[e], obs_ptr[e + 1]
+            if use[b:en].sum() == 0:
+                assert iopt[e] == -1
+                continue
+            corr = np.where(ptype[b:en] == 1, pcorr[stat[b:en] - 1], scorr[stat[b:en] - 1])
+            rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, en - b, 1, use[b:en], stat[b:en], ptype[b:en], corr,
+                                                tori[e:e + 1], var[b:en], tob[b:en], X, Y, Z)
+            assert rc == 0 and io[0] == iopt[e] and ob[0] == obj[e], f"job {job} event {e}"
+            assert np.array_equal(hy, hypo[e]), f"job {job} event {e}"
 
 
 def test_large_catalog_noise_free_round_trip(gpu_ctx):
