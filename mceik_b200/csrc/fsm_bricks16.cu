@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
             const int NI = I + (lane == 0 ? (revx ? 1 : -1) : 0), NJ = J + (lane == 1 ? (revy ? 1 : -1) : 0);
             if (NI >= 0 && NI < a.nbx && NJ >= 0 && NJ < a.nby) up_ptr = done_f + ((K * a.nby + NJ) * a.nbx + NI);
         }
+        // rows of this brick column inside the grid: bricks that are full in y hand their x-face planes on in halves
+        const int x_adj = min(J * kBy + kBy, ny) - J * kBy == kBy ? 2 : -2;
         long long t_upwind = 0;
         // progress of the watched neighbour: `seen` = highest value observed so far (it only grows), `ahead` = an
         // observation issued one chunk earlier whose latency is hidden behind that chunk's arithmetic
@@ -266,9 +268,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                 // lane 0 watches the upwind x neighbour, lane 1 the upwind y neighbour.  A slot's y-halo row is the
                 // neighbour's row By-1 (its slot index is By larger), its x-halo column the neighbour's last
                 // column (slot index only xgroup(7) - xgroup(-1) = 2 larger): x needs By - 2 steps less lead.
-                // Blocked layout: the x-halo comes from the neighbour's face copies, written one whole plane at a
-                // time 16 steps after the plane was entered: x needs 2 steps MORE lead than y.
-                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? -2 : kBy - 2) : 0);
+                // Blocked layout: the x-halo comes from the neighbour's face copies, written in half planes (rows 0..3
+                // 12, rows 4..7 16 steps after the plane was entered): x needs 2 steps less lead than y (2 more
+                // for brick columns cut by the grid's y face, whose planes are written whole).
+                const int need = (s << kProgShift) + steps_needed - (lane == 0 ? (a.blocked ? x_adj : kBy - 2) : 0);
                 seen = max(seen, ahead);
                 if (seen < need)
                     while ((seen = ld_acquire_gpu(up_ptr)) < need) __nanosleep(200);
@@ -394,13 +397,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) sweep_bricks16_kernel(const Br
                            : (size_t)zb * nxy + (size_t)yh * nx + x_lo + 2 * hp;
         }
         // blocked: values of memory columns 0 and 7 go to the face staging FB[field][side][plane & 15][row] when their
-        // pair is written back, and a whole plane of a side (64 contiguous bytes of the record) is stored the step
-        // after its 8 rows are in (so the step's own __syncwarp orders it): 15 steps after the plane was entered for
-        // the side of sweep column 0, 16 for sweep column 7
+        // pair is written back, and half a plane of a side (4 rows, 32 contiguous bytes of the record) is stored the
+        // step after its rows are in (so the step's own __syncwarp orders it): rows 4..7 15 steps after the plane was
+        // entered for the side of sweep column 0, 16 for sweep column 7; rows 0..3 four steps earlier
         const bool face_lane = blocked && (tp == 0 || tp == 3) && act_t;
         const int fb_t = (tp == 0 ? 0 : 1) * (kFacePlanes * kBy) + (yt - y_lo);  // + (plane & 15) * kBy + fi * 2 * kFacePlanes * kBy
         const int fl_side = (lane >> 2) & 1, fl_pair = lane & 3;                 // flush lanes 0..7: side, pair of rows
-        const int fl_lag = ((fl_side == 0) == !revx) ? 15 : 16;                  // memory column 0 is sweep column 0 unless revx
+        // rows 0..3 (in sweep order) of a face plane are complete 4 steps before rows 4..7: each half (32 bytes, one
+        // sector) is stored as soon as it is, so the downwind x neighbour can follow 4 steps closer
+        // (bricks that are full in y; x neighbours share J, hence ey, so both sides of the hand-off agree)
+        const int fl_half = (revy ? 3 - fl_pair : fl_pair) >> 1;                 // 0 = the rows the sweep enters first
+        const int fl_lag = (((fl_side == 0) == !revx) ? 15 : 16) - (fl_half == 0 && ey == kBy ? 4 : 0);  // memory column 0 is sweep column 0 unless revx
         const size_t fl_off = (col * nz + zb) * kRec + kBx * kBy + fl_side * kBy + 2 * fl_pair;
         if (blocked && ey < kBy) {  // rows outside the grid are never written: keep their face entries at u_nan
             for (int e = lane; e < kFaceCells; e += 32) FB[e] = DBL_MAX;
