@@ -90,3 +90,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower(), os.path.join(dirpath, f)
+
+
+def test_c_host_example_compiles_and_links(tmp_path):
+    """tests/c_host_example.c: a plain C driver against include/mceik_b200.h links to the library with gcc; without a
+    B200 it fails loudly (no CPU fallback) instead of computing anything."""
+    import subprocess
+    from test_gpu_c_host import build_c_host
+    exe = build_c_host(tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 1 and "no CPU fallback" in out.stdout
