@@ -252,6 +252,30 @@ def test_blocked_and_natural_layouts(gpu_ctx, natural):
         assert np.array_equal(u[f], ref), f"field {f}: {np.count_nonzero(u[f] != ref)} nodes differ"
 
 
+def test_many_stacked_sources_take_the_generic_brick_kernel(gpu_ctx):
+    """A field with 24 sources stacked along z inside one brick column has boundary-condition nodes on more than 16
+    planes of that brick -- more than the list sweep_bricks16_kernel keeps in shared memory -- so the host routes
+    the solve to the generic brick kernel; a second field with one source rides along.  Bit-equal to the oracle."""
+    from mceik_b200.eikonal import EikonalSolver
+    nx, ny, nz, h = 32, 24, 64, 100.0
+    n = nx * ny * nz
+    slow = cases.checkerboard_slowness(nx, ny, nz, cell=8)
+    ns = 24
+    xs = np.concatenate([np.full(ns, 1234.0), [2020.0]])
+    ys = np.concatenate([np.full(ns, 1111.0), [777.0]])
+    zs = np.concatenate([150.0 + 230.0 * np.arange(ns), [3333.0]])
+    ts = np.concatenate([0.01 * np.arange(ns), [0.0]])
+    src_ptr = np.array([0, ns, ns + 1], np.int32)
+    sol = EikonalSolver(gpu_ctx, nx, ny, nz, h)
+    u, _, iters, ferr = sol.solve_host(slow[None], [0, 0], ts, xs, ys, zs, src_ptr=src_ptr)
+    assert not ferr.any()
+    for f in range(2):
+        a, b = src_ptr[f], src_ptr[f + 1]
+        ref, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, ts[a:b], xs[a:b], ys[a:b], zs[a:b])
+        assert ierr == 0 and it == iters[f]
+        assert np.array_equal(u[f], ref), f"field {f}"
+
+
 def test_solver_building_blocks_selftest(gpu_ctx):
     """sqrt_fast == __dsqrt_rn and the straight-line solver == the reference-ordered solver, bit for
     bit, on 4e8 pseudo-random inputs each (incl. exact squares, ties and u_nan neighbours)."""
