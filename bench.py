@@ -8,8 +8,8 @@
 A *step* is one pass of the eikonal hot path over one batch of synthetic input.  Default = BASELINE config 3:
 64 stations x (P, S) = 128 fields on the 256^3 checkerboard model, solved to convergence (boundary conditions +
 all sweeps + convergence tests) and delivered as fp32 tables; for N > 1 the fields are shared out over the ranks
-by the library (mceik_fsm_solve_sharded_dev: balanced assignment, tables written into the replicated buffer,
-one in-place NCCL all-gather) -- strong scaling.
+by the library (mceik_fsm_solve_sharded_dev: balanced assignment, tables written into the replicated buffer and put
+into the other ranks' copies over NVLink as the fields converge) -- strong scaling.
 `value` = node-updates of all ranks / max-over-ranks device time, inputs resident in HBM.
 `e2e`   = the same through the host-pointer C-ABI call (mceik_fsm_solve_batched_host): pinned host slowness in,
           fp64 fields out, copies inside the timed region.
@@ -95,7 +95,7 @@ def workload_config(a, n_gpus):
     return {"workload": f"BASELINE config 3: fsm3d batched, {a.fields // 2} stations x (P,S) = {a.fields} fields on "
                         f"{a.grid}^3 checkerboard velocity (+-10%, 32-node cells; vs = vp/sqrt3), tol 1e-6, maxit 20, "
                         f"solved to convergence + fp32 tables"
-                        + (" + in-place NCCL all-gather of the tables" if n_gpus > 1 else ""),
+                        + (" + replication of the tables on every GPU (one-sided puts over NVLink as the fields converge)" if n_gpus > 1 else ""),
             "fields_total": a.fields, "fields_per_gpu": per, "grid": [a.grid] * 3,
             "sharding": (f"sources shared out x{n_gpus} by mceik_fsm_assign_fields: fields of a slowness model dealt over the ranks "
                          f"holding it, longest first by the iteration counts of the previous solve") if n_gpus > 1 else "one GPU",
@@ -487,7 +487,10 @@ def run_ours(a):
     ts = np.zeros(nf_tot)
     sol = EikonalSolver(ctx, n, n, n, H, tol=1e-6, maxit=20)
     slots = (nf_tot + world - 1) // world
-    d_tab = torch.empty((world * slots, N), dtype=torch.float32, device="cuda")  # the (replicated) table buffer
+    # the (replicated) table buffer: for N > 1 the library's own, which the other ranks put their tables into over NVLink
+    # as their fields converge (mceik_tables_alloc_replicated)
+    d_tab = (ctx.tables_alloc_replicated(world * slots, N) if world > 1
+             else torch.empty((world * slots, N), dtype=torch.float32, device="cuda"))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if a.config == 2 else None  # 2 x L2
     misfit = C5Misfit(a, ctx, d_tab, fmodel) if a.config == 5 else None
     cost = None
@@ -603,6 +606,9 @@ def run_ours(a):
     events = None
     if a.config == 3 and not a.skip_gs:
         del d_tab
+        if world > 1:
+            barrier()
+            ctx.tables_free_replicated()
         torch.cuda.empty_cache()
         events = run_gs(a, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks)
 

@@ -220,6 +220,15 @@ int mceik_selftest_solver(mceik_ctx *ctx, unsigned long long seed, long long sam
  *                          receives every field's fp32 table at row table_row[f] on every rank; iters / field_ierr
  *                          [nfields] are filled on every rank.  Returns 1 when any field failed its boundary conditions.
  *   mceik_tables_allgather the collective alone (in place: rank r's rows are [r * slots, (r + 1) * slots)).
+ *   mceik_tables_alloc_replicated  collective: one buffer of rows x ldtab floats per rank, every rank mapping the
+ *                          buffers of all the others (CUDA IPC).  When d_tables_all of mceik_fsm_solve_sharded_dev is this
+ *                          buffer, every table is PUT into the peers' copies over NVLink by the copy engines as soon as
+ *                          its field has converged, under the sweeps of the remaining fields: no collective kernel and
+ *                          no rank waiting for another during the solve (the closing all-gather of the iteration counts
+ *                          is the barrier).  The buffer holds a complete set of tables from the return of the solve
+ *                          until any rank starts the next sharded solve into it (the host separates the two with its
+ *                          own barrier when the tables are still in use).  mceik_tables_free_replicated releases it (collective in effect: no rank may
+ *                          still be putting).
  * NCCL is loaded at run time (libnccl.so.2); without it these entry points return -2 and the rest of the library works.
  */
 int mceik_comm_unique_id(void *id128);
@@ -232,6 +241,8 @@ int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
                                 const double *ys, const double *zs, const int *cost, float *d_tables_all, size_t ldtab,
                                 int *iters, int *field_ierr, int *table_row);
 int mceik_tables_allgather(mceik_ctx *ctx, float *d_tables_all, size_t ldtab, int slots);
+int mceik_tables_alloc_replicated(mceik_ctx *ctx, size_t rows, size_t ldtab, float **d_tables_all);
+int mceik_tables_free_replicated(mceik_ctx *ctx);
 
 /* Forward-loop misfit of many proposals (BASELINE config 5; the reference has no code for it, the definition is the
  * build's): model m owns tables [m * ntab, (m + 1) * ntab) of d_tables [nmodels * ntab][ldgrd]; every

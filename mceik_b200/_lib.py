@@ -82,6 +82,8 @@ SIGNATURES = {
     "mceik_fsm_solve_sharded_dev": (C.c_int, [C.c_void_p, C.POINTER(FsmGrid), C.c_int, C.c_void_p, C.c_int, c_int_p, c_int_p,
                                               c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, C.c_void_p, C.c_size_t, c_int_p, c_int_p, c_int_p]),
     "mceik_tables_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "mceik_tables_alloc_replicated": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mceik_tables_free_replicated": (C.c_int, [C.c_void_p]),
     "mceik_fsm_set_algo": (C.c_int, [C.c_void_p, C.c_int]),
     "mceik_fsm_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "mceik_fsm_last_node_updates": (C.c_longlong, [C.c_void_p]),

@@ -34,6 +34,21 @@ class Context:
         _lib.check(self._lib.mceik_comm_init(self.handle, int(world), int(rank), C.c_char_p(bytes(unique_id))), "mceik_comm_init")
         return self
 
+    def tables_alloc_replicated(self, rows, ldtab):
+        """``mceik_tables_alloc_replicated`` (collective): fp32 [rows, ldtab] buffer of this rank that the other ranks
+        put their tables into over NVLink; returned as a torch tensor view (the library owns the memory)."""
+        import torch
+        p = C.c_void_p()
+        _lib.check(self._lib.mceik_tables_alloc_replicated(self.handle, int(rows), int(ldtab), C.byref(p)),
+                   "mceik_tables_alloc_replicated")
+
+        class _View:  # zero-copy: torch reads __cuda_array_interface__
+            __cuda_array_interface__ = {"shape": (int(rows), int(ldtab)), "typestr": "<f4", "data": (p.value, False), "version": 2}
+        return torch.as_tensor(_View(), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def tables_free_replicated(self):
+        _lib.check(self._lib.mceik_tables_free_replicated(self.handle), "mceik_tables_free_replicated")
+
     def comm_destroy(self):
         _lib.check(self._lib.mceik_comm_destroy(self.handle), "mceik_comm_destroy")
 

@@ -52,6 +52,11 @@ struct mceik_ctx {
     // mceik_fsm_solve_batched_host with pinned output: a converged field is copied back on copy_stream while
     // the remaining fields keep iterating (early_u = host destination, early_done[f] = already on its way)
     comm::Comm *comm = nullptr;  // mceik_comm_init: the ranks sharing the sources (one process per GPU)
+    // sharded solve into the replicated buffer (mceik_tables_alloc_replicated): the table of local field f lands in row
+    // put_row0 + f and is put into the peers' buffers on put_stream as soon as the field has converged
+    bool put_enabled = false;
+    size_t put_row0 = 0, put_ldtab = 0, put_n = 0;
+    cudaStream_t put_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     double *early_u = nullptr;
     std::vector<char> early_done;
@@ -425,6 +430,13 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
             const int *d_fin = upload(ctx->ws_meta, o_units, finished, st);
             fsm::launch_unblock_fields(nx, ny, nz, (int)finished.size(), d_fin, d_w, d_u, d_tables, ldtab, st);
         }
+        if (ctx->put_enabled && !finished.empty()) {  // their tables go to the other ranks while the others keep iterating
+            MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, st));
+            MCEIK_CUDA(cudaStreamWaitEvent(ctx->put_stream, ctx->ev_fin, 0));
+            for (int f : finished)
+                comm::put_to_peers(ctx->comm, sizeof(float) * (ctx->put_row0 + (size_t)f) * ctx->put_ldtab, sizeof(float) * ctx->put_n,
+                                   ctx->put_stream);
+        }
         if (ctx->early_u && d_u && !finished.empty()) {  // copy them back while the others keep iterating
             if (blocked) {
                 MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, st));
@@ -576,6 +588,7 @@ void mceik_ctx_destroy(mceik_ctx *c) {
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         if (c->ev_fin) cudaEventDestroy(c->ev_fin);
+        if (c->put_stream) cudaStreamDestroy(c->put_stream);
         try { comm::destroy(c->comm); } catch (...) {}
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -749,6 +762,25 @@ int mceik_fsm_assign_fields(int nfields, const int *field_model, const int *cost
     });
 }
 
+int mceik_tables_alloc_replicated(mceik_ctx *ctx, size_t rows, size_t ldtab, float **d_tables_all) {
+    return guarded([&]() -> int {
+        if (!ctx || !d_tables_all || rows == 0 || ldtab == 0) { set_error("mceik_tables_alloc_replicated: bad argument"); return -1; }
+        DeviceGuard dg(ctx->device);
+        *d_tables_all = static_cast<float *>(comm::alloc_replicated(ctx->comm, sizeof(float) * rows * ldtab, ctx->stream));
+        return 0;
+    });
+}
+
+int mceik_tables_free_replicated(mceik_ctx *ctx) {
+    return guarded([&]() -> int {
+        if (!ctx) return -1;
+        DeviceGuard dg(ctx->device);
+        if (ctx->put_stream) MCEIK_CUDA(cudaStreamSynchronize(ctx->put_stream));
+        comm::free_replicated(ctx->comm);
+        return 0;
+    });
+}
+
 int mceik_tables_allgather(mceik_ctx *ctx, float *d_tables_all, size_t ldtab, int slots) {
     return guarded([&]() -> int {
         if (!ctx || !d_tables_all || slots < 0) { set_error("mceik_tables_allgather: bad argument"); return -1; }
@@ -785,11 +817,34 @@ int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
         const int nl = (int)mine.size();
         std::vector<int> stat(2 * (size_t)slots * world, 0);  // per rank: [iters x slots][ierr x slots]
         int *my = stat.data() + 2 * (size_t)slots * rank;
-        // the tables of the local fields land in this rank's rows of the replicated buffer
-        int rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nl, fm.data(), sp.data(), lts.data(), lxs.data(), lys.data(), lzs.data(), nullptr,
+        // the tables of the local fields land in this rank's rows of the replicated buffer.  In a buffer from
+        // mceik_tables_alloc_replicated every table is put into the peers' copies by the copy engines as soon as its
+        // field has converged (no collective, no rank waits for another); any other buffer is completed by one in-place
+        // all-gather after the solve.
+        const size_t N = (size_t)grid->nx * grid->ny * grid->nz;
+        const bool one_sided = world > 1 && d_tables_all == comm::replicated_local(ctx->comm) &&
+                               sizeof(float) * ldtab * (size_t)slots * world <= comm::replicated_bytes(ctx->comm);
+        if (one_sided) {
+            if (!ctx->put_stream) MCEIK_CUDA(cudaStreamCreateWithFlags(&ctx->put_stream, cudaStreamNonBlocking));
+            ctx->put_enabled = true;
+            ctx->put_row0 = (size_t)rank * slots; ctx->put_ldtab = ldtab; ctx->put_n = N;
+        }
+        int rc;
+        try {
+            rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nl, fm.data(), sp.data(), lts.data(), lxs.data(), lys.data(), lzs.data(), nullptr,
                                d_tables_all + (size_t)rank * slots * ldtab, ldtab, my, my + slots);
+        } catch (...) {
+            ctx->put_enabled = false;
+            throw;
+        }
+        ctx->put_enabled = false;
         if (rc < 0) return rc;
-        comm::all_gather_inplace(ctx->comm, d_tables_all, sizeof(float) * ldtab * (size_t)slots, ctx->stream);
+        if (one_sided) {  // my puts are complete before I contribute to the all-gather below, which therefore is the barrier
+            MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, ctx->put_stream));
+            MCEIK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fin, 0));
+        } else {
+            comm::all_gather_inplace(ctx->comm, d_tables_all, sizeof(float) * ldtab * (size_t)slots, ctx->stream);
+        }
         if (world > 1) {  // iteration counts and error flags of every field, on every rank
             int *d_stat = static_cast<int *>(ctx->ws_comm.ensure(sizeof(int) * stat.size()));
             MCEIK_CUDA(cudaMemcpyAsync(d_stat + 2 * (size_t)slots * rank, my, sizeof(int) * 2 * slots, cudaMemcpyHostToDevice, ctx->stream));

@@ -68,6 +68,10 @@ void check(int rc, const char *what) {
 struct Comm {
     ncclComm_t nccl = nullptr;
     int world = 1, rank = 0;
+    // replicated table buffer (alloc_replicated): this rank's allocation and the peers' mappings of theirs
+    void *rep_local = nullptr;
+    size_t rep_bytes = 0;
+    std::vector<void *> rep_peer;  // [world]; rep_peer[rank] == rep_local
 };
 
 void unique_id(void *out128) {
@@ -90,10 +94,64 @@ Comm *create(int world, int rank, const void *id128) {
     return c;
 }
 
+void free_replicated(Comm *c) {
+    if (!c || !c->rep_local) return;
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->rep_peer[r]) cudaIpcCloseMemHandle(c->rep_peer[r]);
+    cudaFree(c->rep_local);
+    c->rep_local = nullptr;
+    c->rep_bytes = 0;
+    c->rep_peer.clear();
+}
+
 void destroy(Comm *c) {
     if (!c) return;
+    free_replicated(c);
     if (c->nccl) api().CommDestroy(c->nccl);
     delete c;
+}
+
+// One buffer of `bytes` per rank, every rank mapping every other rank's buffer (CUDA IPC; the 64-byte handles travel
+// through an all-gather of the communicator): finished tables are then PUT into the peers' buffers by the copy engines
+// over NVLink (cudaMemcpyAsync on a side stream) while the sweeps of the remaining fields keep the SMs -- no collective
+// kernel, no rank waits for another during the solve.  Collective.
+void *alloc_replicated(Comm *c, size_t bytes, cudaStream_t st) {
+    if (!c) throw CudaError("alloc_replicated: the context has no communicator (mceik_comm_init)");
+    free_replicated(c);
+    MCEIK_CUDA(cudaMalloc(&c->rep_local, bytes));
+    c->rep_bytes = bytes;
+    c->rep_peer.assign(c->world, nullptr);
+    c->rep_peer[c->rank] = c->rep_local;
+    if (c->world == 1) return c->rep_local;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::vector<cudaIpcMemHandle_t> h(c->world);
+    MCEIK_CUDA(cudaIpcGetMemHandle(&h[c->rank], c->rep_local));
+    cudaIpcMemHandle_t *d_h = nullptr;
+    MCEIK_CUDA(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * c->world));
+    MCEIK_CUDA(cudaMemcpyAsync(d_h + c->rank, &h[c->rank], sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, st));
+    all_gather_inplace(c, d_h, sizeof(cudaIpcMemHandle_t), st);
+    MCEIK_CUDA(cudaMemcpyAsync(h.data(), d_h, sizeof(cudaIpcMemHandle_t) * c->world, cudaMemcpyDeviceToHost, st));
+    MCEIK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_h);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        MCEIK_CUDA(cudaIpcOpenMemHandle(&c->rep_peer[r], h[r], cudaIpcMemLazyEnablePeerAccess));
+    }
+    return c->rep_local;
+}
+
+void *replicated_local(const Comm *c) { return c ? c->rep_local : nullptr; }
+size_t replicated_bytes(const Comm *c) { return c ? c->rep_bytes : 0; }
+
+// rows [offset, offset + bytes) of this rank's buffer -> the same place in every peer's buffer (copy engines, `st`)
+void put_to_peers(Comm *c, size_t offset, size_t bytes, cudaStream_t st) {
+    if (!c || c->world == 1 || !c->rep_local) return;
+    if (offset + bytes > c->rep_bytes) throw CudaError("put_to_peers: outside the replicated buffer");
+    for (int k = 1; k < c->world; ++k) {  // start with the next rank: the puts of all ranks spread over all links
+        const int r = (c->rank + k) % c->world;
+        MCEIK_CUDA(cudaMemcpyAsync(static_cast<char *>(c->rep_peer[r]) + offset, static_cast<char *>(c->rep_local) + offset, bytes,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
 }
 
 int world(const Comm *c) { return c ? c->world : 1; }

@@ -1,5 +1,6 @@
 """Two-rank GPU test of the multi-GPU C ABI (mceik_comm_init / mceik_fsm_solve_sharded_dev): every rank ends up with
-every field's fp32 table, bit-equal to the oracle, and with all iteration counts.  Needs two GPUs (skipped
+every field's fp32 table, bit-equal to the oracle, and with all iteration counts -- through the in-place NCCL all-gather
+(caller's buffer) and through one-sided puts into the library's replicated buffer (mceik_tables_alloc_replicated).  Needs two GPUs (skipped
 otherwise; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`)."""
 import numpy as np
 import pytest
@@ -44,6 +45,13 @@ def _worker(rank, world, uid_q, res_q):
         iters, ferr, row = sol.solve_sharded(d_slow, fmodel, np.zeros(nf), xs, ys, zs, d_all, cost=cost)
         ctx.synchronize()
         out.append((iters.copy(), ferr.copy(), row.copy(), d_all.cpu().numpy().copy()))
+    # the library's replicated buffer: tables are put into the peers' copies over NVLink as the fields converge
+    d_rep = ctx.tables_alloc_replicated(world * slots, n)  # (not cleared: a peer may already be putting into it)
+    iters, ferr, row = sol.solve_sharded(d_slow, fmodel, np.zeros(nf), xs, ys, zs, d_rep, cost=None)
+    ctx.synchronize()
+    out.append((iters.copy(), ferr.copy(), row.copy(), d_rep.cpu().numpy().copy()))
+    del d_rep
+    ctx.tables_free_replicated()
     ctx.comm_destroy()
     res_q.put((rank, out))
 
