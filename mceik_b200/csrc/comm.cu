@@ -3,8 +3,10 @@
 // The reference splits ONE field over MPI ranks and exchanges ghost layers every sweep (fsm3d.f90:971-1045), then
 // gathers through rank 0 (fsm3d.f90:1488-1553); its callers hand in a communicator and nothing else
 // (mpiutils.f90:99-264).  Here a field never leaves its GPU: the ranks take whole fields, solve them without any
-// communication, write their fp32 tables straight into their slice of the replicated table buffer and one in-place
-// ncclAllGather over NVLink completes it on every rank.
+// communication and write their fp32 tables straight into their rows of the replicated table buffer.  Replication is
+// one-sided when the buffer is the library's own (alloc_replicated: CUDA IPC mappings of every peer's buffer): a table
+// is put into the peers' copies by the copy engines over NVLink as soon as its field has converged, under the sweeps
+// of the remaining fields.  A caller-owned buffer is completed by one in-place ncclAllGather after the solve.
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2 -- the copy a host such as PyTorch already loaded, else the
 // system one), so libmceik_b200.so has no link-time dependency on it and single-GPU hosts need no NCCL at all.
