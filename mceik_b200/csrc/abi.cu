@@ -182,7 +182,7 @@ int fsm_solve_dev(mceik_ctx *ctx, const mceik_fsm_grid *g, int nmodels, const do
     if (!ctx->ev0) {
         MCEIK_CUDA(cudaEventCreate(&ctx->ev0));
         MCEIK_CUDA(cudaEventCreate(&ctx->ev1));
-        MCEIK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming));
+        if (!ctx->ev_fin) MCEIK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming));
     }
 
     ctx->plan.build(nx, ny, nz, st);
@@ -826,6 +826,7 @@ int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
                                sizeof(float) * ldtab * (size_t)slots * world <= comm::replicated_bytes(ctx->comm);
         if (one_sided) {
             if (!ctx->put_stream) MCEIK_CUDA(cudaStreamCreateWithFlags(&ctx->put_stream, cudaStreamNonBlocking));
+            if (!ctx->ev_fin) MCEIK_CUDA(cudaEventCreateWithFlags(&ctx->ev_fin, cudaEventDisableTiming));  // a rank without fields never solves
             ctx->put_enabled = true;
             ctx->put_row0 = (size_t)rank * slots; ctx->put_ldtab = ldtab; ctx->put_n = N;
         }
