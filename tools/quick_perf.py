@@ -25,7 +25,7 @@ ap.add_argument("--gs-n", type=int, default=128)
 ap.add_argument("--gs-stations", type=int, default=32)
 ap.add_argument("--gs-events", type=int, default=512)
 ap.add_argument("--skip-fsm", action="store_true")
-ap.add_argument("--algo", type=int, default=0)
+ap.add_argument("--algo", type=int, default=2)  # 2 = brick kernels (the product default), 0 = tiles, 1 = levels
 ap.add_argument("--skip-gs", action="store_true")
 ap.add_argument("--maxit", type=int, default=20)
 a = ap.parse_args()
