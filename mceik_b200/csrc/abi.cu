@@ -830,16 +830,23 @@ int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
             ctx->put_enabled = true;
             ctx->put_row0 = (size_t)rank * slots; ctx->put_ldtab = ldtab; ctx->put_n = N;
         }
-        int rc;
-        try {
-            rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nl, fm.data(), sp.data(), lts.data(), lxs.data(), lys.data(), lzs.data(), nullptr,
-                               d_tables_all + (size_t)rank * slots * ldtab, ldtab, my, my + slots);
-        } catch (...) {
-            ctx->put_enabled = false;
-            throw;
+        // A rank whose own solve fails (bad argument, CUDA error) still takes part in the collectives below -- the
+        // others would wait for it forever -- and marks its fields with ierr = -1; it reports the failure afterwards.
+        int rc = 0;
+        std::string local_error;
+        if (nl > 0) {  // (a rank without fields has nothing to solve: more ranks than fields)
+            try {
+                rc = fsm_solve_dev(ctx, grid, nmodels, d_slow, nl, fm.data(), sp.data(), lts.data(), lxs.data(), lys.data(), lzs.data(),
+                                   nullptr, d_tables_all + (size_t)rank * slots * ldtab, ldtab, my, my + slots);
+                if (rc < 0) local_error = mceik_last_error();
+            } catch (const std::exception &e) {
+                rc = -2;
+                local_error = e.what();
+            }
         }
         ctx->put_enabled = false;
-        if (rc < 0) return rc;
+        if (rc < 0)
+            for (int i = 0; i < nl; ++i) my[slots + i] = -1;
         if (one_sided) {  // my puts are complete before I contribute to the all-gather below, which therefore is the barrier
             MCEIK_CUDA(cudaEventRecord(ctx->ev_fin, ctx->put_stream));
             MCEIK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_fin, 0));
@@ -861,6 +868,10 @@ int mceik_fsm_solve_sharded_dev(mceik_ctx *ctx, const mceik_fsm_grid *grid, int 
             if (field_ierr) field_ierr[f] = e;
             any |= e;
             if (table_row) table_row[f] = row[f];
+        }
+        if (rc < 0) {
+            set_error("mceik_fsm_solve_sharded_dev: the solve of rank %d failed: %s", rank, local_error.c_str());
+            return rc;
         }
         return any ? 1 : 0;
     });

@@ -52,8 +52,18 @@ def _worker(rank, world, uid_q, res_q):
     out.append((iters.copy(), ferr.copy(), row.copy(), d_rep.cpu().numpy().copy()))
     del d_rep
     ctx.tables_free_replicated()
+    # fewer fields than ranks: rank 1 solves nothing and still ends up with the table, by either replication path
+    one = []
+    d_one = torch.zeros((world, n), dtype=torch.float32, device="cuda")
+    d_rep1 = ctx.tables_alloc_replicated(world, n)
+    for buf in (d_one, d_rep1):
+        iters, ferr, row = sol.solve_sharded(d_slow, fmodel[:1], np.zeros(1), xs[:1], ys[:1], zs[:1], buf, cost=None)
+        ctx.synchronize()
+        one.append((iters.copy(), ferr.copy(), row.copy(), buf.cpu().numpy().copy()))
+    del d_rep1, buf
+    ctx.tables_free_replicated()
     ctx.comm_destroy()
-    res_q.put((rank, out))
+    res_q.put((rank, out, one))
 
 
 def test_sharded_solve_two_ranks():
@@ -68,7 +78,20 @@ def test_sharded_solve_two_ranks():
     procs = [ctx.Process(target=_worker, args=(r, 2, uid_q, res_q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(res_q.get(timeout=600) for _ in procs)
+    import queue
+    import time
+    got, t_end = [], time.time() + 240
+    while len(got) < len(procs):  # a worker that died would leave its peer waiting in a collective: fail at once
+        try:
+            got.append(res_q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() > t_end:
+                for p in procs:
+                    p.kill()
+                pytest.fail(f"sharded workers: exit codes {[p.exitcode for p in procs]}" if dead else "sharded workers timed out")
+    res = {r: out for r, out, _ in got}
+    res_one = {r: one for r, _, one in got}
     for p in procs:
         p.join(timeout=120)
     for rank in (0, 1):
@@ -78,5 +101,9 @@ def test_sharded_solve_two_ranks():
                 u, ierr, it = ref[f]
                 assert ierr == 0 and iters[f] == it, (rank, f)
                 assert np.array_equal(tabs[row[f]], u.astype(np.float32)), (rank, f)
+        for iters, ferr, row, tabs in res_one[rank]:
+            u, ierr, it = ref[0]
+            assert not ferr.any() and iters[0] == it and row[0] == 0
+            assert np.array_equal(tabs[0], u.astype(np.float32)), rank
     # both ranks computed the same assignment
     assert all(np.array_equal(a[2], b[2]) for a, b in zip(res[0], res[1]))

@@ -95,3 +95,8 @@ def test_field_assignment_of_the_c_abi():
     # a single rank
     rk5, row5, sl5 = sharding.assign_fields(fm, 1)
     assert sl5 == 7 and not rk5.any() and list(row5) == list(range(7))
+    # fewer fields than ranks: some ranks get nothing, every rank still owns `slots` rows
+    rk6, row6, sl6 = sharding.assign_fields(np.array([3, 3, 5], np.int32), 8)
+    assert sl6 == 1 and len(set(rk6)) == 3 and np.array_equal(row6, rk6)
+    rk7, row7, sl7 = sharding.assign_fields(np.zeros(0, np.int32), 4)
+    assert sl7 == 0 and len(rk7) == 0 and len(row7) == 0
