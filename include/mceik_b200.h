@@ -219,6 +219,10 @@ int mceik_selftest_solver(mceik_ctx *ctx, unsigned long long seed, long long sam
  *                          rank (d_slow: every model resident on every rank).  d_tables_all [world * slots][ldtab]
  *                          receives every field's fp32 table at row table_row[f] on every rank; iters / field_ierr
  *                          [nfields] are filled on every rank.  Returns 1 when any field failed its boundary conditions.
+ *                          With more ranks than fields some ranks solve nothing and still receive every table.  A
+ *                          rank whose own solve fails (< 0, mceik_last_error) still takes part in the closing
+ *                          collectives, so the others return (1, with field_ierr = -1 for that rank's fields)
+ *                          instead of waiting for it.
  *   mceik_tables_allgather the collective alone (in place: rank r's rows are [r * slots, (r + 1) * slots)).
  *   mceik_tables_alloc_replicated  collective: one buffer of rows x ldtab floats per rank, every rank mapping the
  *                          buffers of all the others (CUDA IPC).  When d_tables_all of mceik_fsm_solve_sharded_dev is this
