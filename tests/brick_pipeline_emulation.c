@@ -28,7 +28,16 @@
  * (an update whose inputs did not change is idempotent).  The model reports how many brick sweeps that skips and
  * must still give the oracle's bits.
  *
- * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead [skip [checkerboard cell]]]  -> "MATCH iters=<k> stalls=<n> ..." or "MISMATCH ..."
+ * Blocked layout (argv[9] = 1; the kernel's default data path): the x halo of a brick is not read from the field but
+ * from FACE COPIES -- per brick column and plane, the values of its memory columns 0 and 7 -- which the owning brick
+ * stores itself, in half planes: the four rows its sweep enters first 11 (sweep column 0) / 12 (sweep column 7)
+ * steps after the plane was entered, the other four 15 / 16 steps after (brick columns cut by the grid's y face:
+ * all rows 15 / 16).  The upwind x neighbour must then have completed m + By + 3 steps before slot m is loaded
+ * (m + By + 7 for cut columns); at the grid's x faces a brick reads its own face copy.  The model checks that every
+ * face value stored was final (written back in an earlier step), that an upwind face value read belongs to the
+ * current sweep, and that own / downwind face values read are still those of the previous sweep.
+ *
+ * Usage: brick_pipeline_emulation nx ny nz zc seed [dlead [skip [checkerboard cell [blocked]]]]  -> "MATCH iters=<k> stalls=<n> ..." or "MISMATCH ..."
  */
 #include <float.h>
 #include <math.h>
@@ -72,7 +81,12 @@ static double h;
 static const double *slow;
 static const unsigned char *lisbc;
 static double *u;
-static int lead_x, lead_y;
+static int lead_x, lead_y, dlead_g;
+static int blocked;         /* 1 = x halo from face copies (the kernel's blocked layout) */
+static double *face;        /* [side][brick column J * nbx + I][gz][row] values of memory columns 0 / 7 */
+static long *face_sweep;    /* global sweep in which the entry was last stored (-1: by the boundary conditions) */
+static long face_not_final, face_stale, face_early;
+#define FIDX(side, I, J, gz, row) (((((long)(side) * nby + (J)) * nbx + (I)) * nz + (gz)) * BY + (row))
 #define REVX(s) ((s) & 1)
 #define REVY(s) (((s) >> 1) & 1)
 #define REVZ(s) (((s) >> 2) & 1)   /* fsm3d.f90:46-53 */
@@ -105,7 +119,9 @@ static int may_load(brick_t *bk, const brick_t *b, int m)
     const int sw = b->sweep;
     const brick_t *ux = brick_at(bk, b->I + (REVX(sw) ? 1 : -1), b->J, b->K);
     const brick_t *uy = brick_at(bk, b->I, b->J + (REVY(sw) ? 1 : -1), b->K);
-    if (ux && word(ux) < (sw << 12) + m + lead_x) return 0;
+    /* blocked: the x halo comes out of the neighbour's face copies, stored in half planes (whole planes when cut in y) */
+    const int lx = blocked ? (b->ey == BY ? BY + 3 : BY + 7) + dlead_g : lead_x;
+    if (ux && word(ux) < (sw << 12) + m + lx) return 0;
     if (uy && word(uy) < (sw << 12) + m + lead_y) return 0;
     return 1;
 }
@@ -148,7 +164,21 @@ static void load_slot(brick_t *b, int m)
         for (int j = -1; j <= b->ey; j++)
             for (int i = -1; i <= BX; i++)
                 if (xgroup(i) + (j + 1) + (k + 1) == m) {
-                    b->L[LIDX(b, i, j, k)] = u[gnode(b, i, j, k)];
+                    double v = u[gnode(b, i, j, k)];
+                    if (blocked && (i == -1 || i == BX) && j >= 0 && j < b->ey && k >= 0 && k < b->ez) {
+                        const int sw = b->sweep;
+                        const int gx = REVX(sw) ? b->x_lo + BX - 1 - i : b->x_lo + i;   /* not clamped */
+                        const int gy = REVY(sw) ? b->y_hi - j : b->y_lo + j, gz = REVZ(sw) ? b->z_hi - k : b->z_lo + k;
+                        int In = b->I, side;
+                        if (gx >= 0 && gx < nx) { In = gx / BX; side = (gx % BX == 0) ? 0 : 1; }  /* the neighbour's adjacent column */
+                        else side = gx < 0 ? 0 : 1;                                              /* grid face: own boundary column */
+                        const long fi = FIDX(side, In, b->J, gz, gy - b->y_lo);
+                        v = face[fi];
+                        const long G = gsweep0 + sw;
+                        if (In != b->I && i == -1) { if (face_sweep[fi] != G) face_stale++; }     /* upwind: this sweep's value */
+                        else if (face_sweep[fi] == G) face_early++;                               /* own / downwind: not yet */
+                    }
+                    b->L[LIDX(b, i, j, k)] = v;
                     b->have[LIDX(b, i, j, k)] = 1;
                 }
     b->loaded = m;
@@ -187,6 +217,24 @@ static void step(brick_t *b)
         for (int j = 0; j < b->ey; j++)
             for (int i = 0; i < BX; i++)
                 if (xgroup(i) + (j + 1) + (k + 1) == l - 4) u[gnode(b, i, j, k)] = b->L[LIDX(b, i, j, k)];
+    if (blocked) {  /* face planes: half planes of each side, a fixed number of steps after the plane was entered */
+        const int sw = b->sweep;
+        for (int side = 0; side < 2; side++)
+            for (int half = 0; half < 2; half++) {
+                const int is = ((side == 0) == !REVX(sw)) ? 0 : BX - 1;          /* sweep column of this memory column */
+                const int lag = (is == 0 ? 15 : 16) - ((half == 0 && b->ey == BY) ? 4 : 0);
+                const int kf = l - lag;
+                if (kf < 0 || kf >= b->ez) continue;
+                const int j0 = b->ey == BY ? 4 * half : (half ? b->ey : 0), j1 = b->ey == BY ? 4 * half + 4 : b->ey;
+                for (int j = j0; j < j1; j++) {
+                    if (xgroup(is) + (j + 1) + (kf + 1) > l - 5) face_not_final++;  /* written back before this step? */
+                    const int gy = REVY(sw) ? b->y_hi - j : b->y_lo + j, gz = REVZ(sw) ? b->z_hi - kf : b->z_lo + kf;
+                    const long fi = FIDX(side, b->I, b->J, gz, gy - b->y_lo);
+                    face[fi] = b->L[LIDX(b, is, j, kf)];
+                    face_sweep[fi] = gsweep0 + sw;
+                }
+            }
+    }
     b->progress = l + 1;
 }
 
@@ -198,11 +246,15 @@ static long iteration(brick_t *bk, long nb, unsigned *rng)
         *rng = *rng * 1664525u + 1013904223u;
         brick_t *b = bk + (*rng >> 8) % nb;
         if (b->sweep == 8) continue;
-        const int nsteps = b->ez + BY + 7;
+        const int nsteps = b->ez + BY + 7 + (blocked ? 1 : 0);  /* blocked: one more step stores the last face plane */
         int moved = 0;
         if (b->loaded < 0) {  /* start of a sweep: slots 0 .. AHEAD-1 */
             const int sk = (skip_mode && may_start(bk, b)) ? may_skip(bk, b) : 0;
             if (sk == 1) {
+                if (blocked)  /* nothing changes, so the face copies of the previous sweep are this sweep's too */
+                    for (int side = 0; side < 2; side++)
+                        for (int gz = b->z_lo; gz <= b->z_hi; gz++)
+                            for (int row = 0; row < b->ey; row++) face_sweep[FIDX(side, b->I, b->J, gz, row)] = gsweep0 + b->sweep;
                 b->sweep++; skipped++; tasks++;
                 if (b->sweep == 8) left--;
                 moved = 1;
@@ -235,7 +287,8 @@ int main(int argc, char **argv)
     unsigned rng = argc > 5 ? (unsigned)atoi(argv[5]) : 1u;
     const int dlead = argc > 6 ? atoi(argv[6]) : 0;
     skip_mode = argc > 7 ? atoi(argv[7]) : 0;
-    lead_x = 7 + dlead; lead_y = BY + 5 + dlead;
+    lead_x = 7 + dlead; lead_y = BY + 5 + dlead; dlead_g = dlead;
+    blocked = argc > 9 ? atoi(argv[9]) : 0;
     if (nx % BX) { printf("nx must be a multiple of 8\n"); return 2; }
     nxy = (long)nx * ny;
     long n = nxy * nz;
@@ -280,6 +333,16 @@ int main(int argc, char **argv)
         b->have = malloc((size_t)(BX + 2) * (BY + 2) * (b->ez + 2));
         b->last_changed = 7;   /* "changed in the sweep before the first one": nothing is skipped at the start */
     }
+    if (blocked) {  /* face copies of the boundary-condition state (apply_bcs_blocked_kernel writes them too) */
+        face = malloc(sizeof(double) * 2 * nbx * nby * nz * BY);
+        face_sweep = malloc(sizeof(long) * 2 * nbx * nby * nz * BY);
+        for (int side = 0; side < 2; side++) for (int J = 0; J < nby; J++) for (int I = 0; I < nbx; I++)
+            for (int gz = 0; gz < nz; gz++) for (int row = 0; row < BY; row++) {
+                const int gy = J * BY + row;
+                face[FIDX(side, I, J, gz, row)] = gy < ny ? u[(long)gz * nxy + (long)gy * nx + I * BX + (side ? BX - 1 : 0)] : DBL_MAX;
+                face_sweep[FIDX(side, I, J, gz, row)] = -1;
+            }
+    }
     long stalls = 0;
     int it;
     for (it = 1; it <= maxit; it++) {
@@ -293,10 +356,11 @@ int main(int argc, char **argv)
     if (it > maxit) it = maxit;
     long bad = 0;
     for (long i = 0; i < n; i++) if (u[i] != uref[i]) bad++;
-    if (bad || it != ref_iters || ring_violations || unloaded_reads)
-        printf("MISMATCH nodes=%ld iters=%d ref_iters=%d ring_violations=%ld unloaded_reads=%ld\n", bad, it, ref_iters,
-               ring_violations, unloaded_reads);
+    const long face_bad = face_not_final + face_stale + face_early;
+    if (bad || it != ref_iters || ring_violations || unloaded_reads || face_bad)
+        printf("MISMATCH nodes=%ld iters=%d ref_iters=%d ring_violations=%ld unloaded_reads=%ld face: not_final=%ld stale=%ld early=%ld\n",
+               bad, it, ref_iters, ring_violations, unloaded_reads, face_not_final, face_stale, face_early);
     else
         printf("MATCH iters=%d stalls=%ld skipped=%ld of %ld brick sweeps\n", it, stalls, skipped, tasks);
-    return (bad || it != ref_iters || ring_violations || unloaded_reads) ? 1 : 0;
+    return (bad || it != ref_iters || ring_violations || unloaded_reads || face_bad) ? 1 : 0;
 }
