@@ -10,9 +10,12 @@
  * vector for the FSM (its only numeric check, fsm3d.f90:2149-2164, is dead code behind
  * `goto 500` at fsm3d.f90:2148) and there is no Fortran compiler in the build container,
  * so this restatement is pinned only by (a) by-construction facts checked in
- * tests/test_oracle_fsm.py (source-node values, monotonicity, first-order agreement with
- * the analytic homogeneous field the reference meant to compare with) and (b) a line by
- * line reading of the Fortran.  Each function cites the lines it restates.
+ * tests/test_oracle_golden.py (source-node values, monotonicity, first-order agreement with
+ * the analytic homogeneous field the reference meant to compare with), (b) a line by
+ * line reading of the Fortran, and (c) a second reading of the same Fortran lines in
+ * another language (tests/fsm_restatement.py, plain Python floats), with which it agrees
+ * bit for bit on fields, error codes and iteration counts.  Each function cites the
+ * lines it restates.
  *
  * Arithmetic contract (what "bit-exact" means for the CUDA path):
  *   - reference flags are gfortran -O2 without -march (Makefile.inc:4-13): separate

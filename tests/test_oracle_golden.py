@@ -153,6 +153,51 @@ def test_fsm_golden_regression_and_properties():
     assert np.all(u < 1e300) and np.all(u >= 0.0)
 
 
+@pytest.mark.parametrize("case", ["random_two_sources", "checkerboard_source_on_a_node", "offset_origin_maxit",
+                                  "source_near_the_far_corner", "source_on_node_1_fails"])
+def test_fsm_oracle_equals_a_second_reading_of_the_reference(case):
+    """No Fortran compiler exists here or on the GPU boxes, so the C oracle cannot be pinned against the compiled
+    reference.  tests/fsm_restatement.py restates the same fsm3d.f90 lines a second time (plain Python floats: IEEE
+    doubles, no FMA, correctly rounded sqrt); the two readings must agree bit for bit on fields, error codes and
+    iteration counts."""
+    import cases
+    import fsm_restatement as R
+    tol, maxit, x0, y0, z0 = 1e-6, 20, 0.0, 0.0, 0.0
+    if case == "random_two_sources":
+        nx, ny, nz, h = 13, 11, 9, 100.0
+        slow = cases.random_slowness(nx * ny * nz, seed=17)
+        ts, xs, ys, zs = [0.0, 0.3], [h * 4.37, h * 10.2], [h * 6.61, h * 2.0], [h * 3.45, h * 6.5]
+    elif case == "checkerboard_source_on_a_node":  # the three-node stencil of EIKONAL_INIT_GRID's ELSE branch
+        nx, ny, nz, h = 12, 10, 14, 250.0
+        slow = cases.checkerboard_slowness(nx, ny, nz, cell=4)
+        ts, xs, ys, zs = [0.0], [h * 5.0], [h * 4.0], [h * 7.0]
+    elif case == "offset_origin_maxit":            # non-zero grid origin, stopped by maxit before convergence
+        nx, ny, nz, h = 10, 12, 8, 50.0
+        slow = cases.random_slowness(nx * ny * nz, seed=3)
+        x0, y0, z0, maxit = -120.0, 35.5, 1000.0, 2
+        ts, xs, ys, zs = [1.5], [x0 + h * 2.7], [y0 + h * 9.1], [z0 + h * 4.4]
+    elif case == "source_near_the_far_corner":     # stencil against the upper grid faces, clamped neighbours
+        nx, ny, nz, h = 9, 9, 9, 100.0
+        slow = cases.random_slowness(nx * ny * nz, seed=5)
+        ts, xs, ys, zs = [0.0], [h * 7.6], [h * 7.2], [h * 7.9]
+    else:                                          # node 1 needs node 0: SETBCS fails, nothing is solved
+        nx, ny, nz, h = 8, 8, 8, 100.0
+        slow = cases.random_slowness(nx * ny * nz, seed=9)
+        ts, xs, ys, zs = [0.0], [0.0], [h * 3.3], [h * 4.1]
+    ref, ierr_ref, it_ref = R.serial_driver(nx, ny, nz, h, list(map(float, slow)), ts, xs, ys, zs, tol=tol, maxit=maxit,
+                                            x0=x0, y0=y0, z0=z0)
+    u, ierr, it = O.eikonal_serial(nx, ny, nz, h, slow, ts, xs, ys, zs, tol=tol, maxit=maxit, x0=x0, y0=y0, z0=z0)
+    if case == "source_on_node_1_fails":
+        assert ierr_ref == 1 and ierr == 1
+        return
+    assert ierr == ierr_ref == 0 and it == it_ref
+    assert np.array_equal(u, np.array(ref)), f"{np.count_nonzero(u != np.array(ref))} nodes differ"
+    if case == "offset_origin_maxit":
+        assert it == 2
+    else:
+        assert 2 <= it < 20
+
+
 def test_fsm_source_stencil_quirks():
     """EIKONAL_INIT_GRID (fsm3d.f90:716-755): a source on node 1 or outside the grid fails; on node nx-1
     it keeps 2 nodes along that axis; EIKONAL_SOURCE_INDEX rounds to the nearest node."""
