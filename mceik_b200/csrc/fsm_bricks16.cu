@@ -7,8 +7,12 @@
 //     = the 64 nodes of a brick plane (512 contiguous bytes) + copies of its columns 0 and 7.  A brick walk of the
 //     caller's [z][y][x] layout reads 64-byte pieces at a 2 KB stride, which the DRAM serves at 4.4 TB/s at most, and
 //     pays 8 sectors per side and plane for its x halo; here the walk is sequential and the x halo is the neighbour's
-//     face copy.  The kernel keeps the copies up to date itself (face staging ring FB, one 64-byte store per plane
-//     and side).  The [z][y][x] layout remains available (blocked = 0; tuning key NATURAL).
+//     face copy.  The kernel keeps the copies up to date itself (face staging ring FB; a side's plane is stored in
+//     halves, 32 bytes = one sector as soon as its four rows are final, so the downwind x neighbour follows four
+//     steps closer).  The [z][y][x] layout remains available (blocked = 0; tuning key NATURAL).
+//   * a step has ONE __syncwarp, at its top; the neighbour reads, the write-back of the slot that became final in
+//     the previous step, the copies six slots ahead, the face store and the two update chains are one region the
+//     compiler interleaves (tests/brick_pipeline_emulation.c models the schedule, blocked layout included).
 //   * every global <-> shared transfer of nodes moves a PAIR of x-adjacent nodes (16 bytes): cp.async.cg (L2 only)
 //     and 128-bit stores -- 2 copies + 1 halo copy (24 lanes) + 1 store per lane and step.
 //   * a ring row keeps the brick's x order of MEMORY (column q = x - x_lo at cell q + 2 of a 10-cell row), whatever
@@ -55,7 +59,7 @@ constexpr int kMaxZc = 256;
 constexpr int kProgShift = 12;
 constexpr int kLead = kBy + 4;                     // a slot is stored 4 steps after it was entered: slot m + By is in memory once m + By + 5 steps are done
 constexpr int kRec = kBx * kBy + 2 * kBy;          // blocked layout: doubles per brick plane (64 nodes + the two x-face copies)
-constexpr int kFacePlanes = 16;                    // planes of the face staging ring (a plane is written over 9 steps, stored the step after)
+constexpr int kFacePlanes = 16;                    // planes of the face staging ring (a plane is written over 9 steps, its halves stored 11..16 steps after it was entered)
 constexpr int kBcMax = 16;                         // planes of one brick that hold boundary-condition nodes of one field
 // Fields walked per task.  A flavour with two fields of one slowness model per task (slots side by side, slowness tile
 // loaded once, 4 update chains per lane, 8 warps per SM) was built and measured slower at every field count
