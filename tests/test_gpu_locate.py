@@ -204,6 +204,46 @@ def test_batched_ragged_catalog(gpu_ctx):
             assert ob[0] == obj[e] and hy[3] == t0[e]
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_two_picks_of_one_table_in_an_event(gpu_ctx, ragged):
+    """The same station and phase picked twice in one event (two analysts): both picks enter the sums, in catalogue
+    order.  Uniform blocks (every event lists the same tables, duplicate included: fast kernel) and ragged, sorted
+    ones (a repeated table is not strictly increasing, so the block stays on the general kernel).  Equal to the
+    oracle bit for bit."""
+    from mceik_b200.locate import Locator
+    n, h, tables, _ = _c1_case(nevents=1, n=24, nstat=6)
+    ngrd = n ** 3
+    ntab = tables.shape[0]
+    rng = np.random.default_rng(7 + ragged)
+    ne = 19
+    base = sorted(rng.permutation(ntab)[:7].tolist())
+    base = base[:3] + [base[2]] + base[3:]          # table base[2] twice in a row
+    obs_ptr, tid, tc, var, tori = [0], [], [], [], rng.uniform(0, 5, ne)
+    for e in range(ne):
+        ids = list(base)
+        if ragged and e % 3 == 1:
+            ids = ids[1:]                           # another subset, still sorted with the duplicate
+        node = int(rng.integers(0, ngrd))
+        for t in ids:
+            tid.append(int(t))
+            tc.append(float(tables[t, node]) + tori[e] + rng.normal(0, 0.03))
+            var.append(float(rng.choice([0.1, 0.25, 0.5])))
+        obs_ptr.append(len(tid))
+    obs_ptr, tid, tc, var = np.array(obs_ptr, np.int32), np.array(tid, np.int32), np.array(tc), np.array(var)
+    loc = Locator(gpu_ctx)
+    loc.set_tables_host(tables, ngrd)
+    for job in (2, 1):
+        iopt, t0, obj = loc.locate_host(job, obs_ptr, tid, tc, var, tori)
+        for e in range(ne):
+            b, en = obs_ptr[e], obs_ptr[e + 1]
+            k = en - b
+            stat, ph = (tid[b:en] // 2 + 1).astype(np.int32), (tid[b:en] % 2 + 1).astype(np.int32)
+            rc, hy, io, ob = O.locate3d_catalog(job, ngrd, ngrd, tables, k, 1, np.ones(k, np.int32), stat, ph, np.zeros(k),
+                                                tori[e:e + 1], var[b:en], tc[b:en], np.zeros(ngrd), np.zeros(ngrd), np.zeros(ngrd))
+            assert rc == 0 and io[0] == iopt[e], f"event {e}"
+            assert ob[0] == obj[e] and hy[3] == t0[e]
+
+
 def test_ragged_sorted_catalog_is_aligned_onto_the_fast_kernel(gpu_ctx):
     """Events with different subsets of the tables, picks in increasing table order (a station-ordered catalogue):
     the host entry re-lays each block of 8 events out over the union of its tables so the branch-free kernel runs it;
